@@ -1,0 +1,195 @@
+/*
+ * libsfb200 — C-ABI of the B200-native ShapeFormer hot path (sm_100a).
+ *
+ * The reference (QhelDIV/ShapeFormer) is pure Python/PyTorch and has NO native interface; these entry points are what a
+ * ctypes binding on the reference side would call to replace the functions listed beside each one (paths relative to
+ * /root/reference/shapeformer/models/).  INTEGRATION.md shows the binding.
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer borrowed from the caller (torch `data_ptr()`), kept alive by the caller;
+ *   - the library never allocates device memory, never synchronises, never throws; all work is enqueued on `stream`
+ *     (a `cudaStream_t` passed as void*);
+ *   - return value 0 = ok, negative = SFB200_E_* (see sfb200_error_string); CUDA launch errors are returned as
+ *     SFB200_E_CUDA with the message available from sfb200_last_cuda_error();
+ *   - indices are int64 (the reference's torch.long), activations / weights fp32, row-major contiguous.
+ */
+#ifndef SFB200_H
+#define SFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFB200_VERSION 100
+
+#define SFB200_OK 0
+#define SFB200_E_ARG (-1)      /* invalid argument / unsupported shape */
+#define SFB200_E_CUDA (-2)     /* CUDA runtime error (see sfb200_last_cuda_error) */
+#define SFB200_E_STATE (-3)    /* call order violated (e.g. step before prefill) */
+
+int sfb200_version(void);
+const char *sfb200_error_string(int code);
+const char *sfb200_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * VQDIF decoder side  (vqdif/vqdif.py:60-76, vqdif/dec.py:62-100, vqdif/quantizer.py:19-30)
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* Quantizer.get_code (vqdif/quantizer.py:19-30): out[b][c][cell] = codebook[code_ind[b][cell]][c].
+ * code_ind (B, cells) int64 in [0, n_codes), codebook (n_codes, C) fp32, out (B, C, cells) fp32 (= BCDHW). */
+int sfb200_code_gather(const int64_t *code_ind, const float *codebook, float *out, int B, int cells, int C, int n_codes,
+                       void *stream);
+
+/* Layout change of the decoder's feature grid, (B, C, S) channel-first -> (B, S, C) channel-last (S = D*H*W), so that one
+ * trilinear corner is one contiguous C*4-byte read in sfb200_decoder_points. */
+int sfb200_grid_to_channels_last(const float *src, float *dst, int B, int C, int64_t S, void *stream);
+
+/* Number of floats of the packed LocalDecoder MLP weights (hidden = c_dim = 32, n_blocks = 5): see
+ * shapeformer_b200/models/vqdif/dec.py::pack_mlp_weights for the order. */
+#define SFB200_DEC_HIDDEN 32
+#define SFB200_DEC_BLOCKS 5
+#define SFB200_DEC_MLP_FLOATS (32 * 3 + 32 + 5 * (3 * (32 * 32 + 32)) + 32 + 1)
+
+/* Upload the packed MLP weights (device pointer, SFB200_DEC_MLP_FLOATS floats) into the library's constant bank for the
+ * current device.  Must be called (on `stream`) before sfb200_decoder_points whenever the weights change. */
+int sfb200_decoder_set_weights(const float *mlp_weights, void *stream);
+
+/* LocalDecoder.forward minus the conv prologue (vqdif/dec.py:85-97; normalize_3d_coordinate vqdif/common.py:260-276;
+ * ResnetBlockFC vqdif/layers.py:39-48), including VQDIF.decode's Xtg/2 (vqdif/vqdif.py:71):
+ *   grid   (B, R, R, R, 32) fp32 channel-last feature grid (output of UNet3D+Upsampler),
+ *   xtg    (B or 1, N, 3) fp32 query points in [-1,1]; xtg_batch_stride = N*3 or 0 when shared by all shapes,
+ *   logits (B, N) fp32 occupancy logits (the reference's (B,N,1)).
+ * impl: 0 = default (tcgen05 split-bf16 tensor-core kernel), 1 = fp32 FFMA kernel (verification / small N). */
+int sfb200_decoder_points(const float *grid, const float *xtg, int64_t xtg_batch_stride, float *logits, int B, int R,
+                          int64_t N, int impl, void *stream);
+
+/* filter_end_tokens + batch_sparse2dense (shapeformer/common.py:50-55,171-189; caller shapeformer/shapeformer.py:342-351):
+ * dense[b][:] = empty_index[b]; for t in order: if pos,val are not end tokens: dense[b][pos] = val (later writes win).
+ * tokens (B, T, 2) int64, empty_index (B) int64, dense (B, cells) int64. */
+int sfb200_tokens_to_dense(const int64_t *tokens, const int64_t *empty_index, int64_t *dense, int B, int T, int cells,
+                           int64_t end_pos, int64_t end_val, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Autoregressive sampler  (shapeformer/shapeformer.py:54-123, transformer/mingpt.py:46-111,185-319,
+ *                          shapeformer/representers.py:120-155,187-196,432-442, shapeformer/common.py:260-299)
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+typedef struct sfb200_ar_config {
+    /* model shape — CondTupleGPT.__init__ (transformer/mingpt.py:187-244) */
+    int n_embd;          /* 1024; multiple of 64 */
+    int n_head;          /* 16; head dim must be 64 */
+    int n_layers[2];     /* {20, 4} */
+    int block_size;      /* 812 */
+    int vocab[2];        /* {4097, 4097}  (<= 8192) */
+    int extra_vocab;     /* 4097 */
+    int64_t end_tokens[2]; /* {4096, 4096} */
+    /* run shape */
+    int max_rows;        /* B: rows sampled together */
+    int max_len;         /* KV-cache capacity in positions (>= L_cond + max_steps) */
+    int max_steps;       /* capacity of the logits history */
+    int prefill_rows;    /* rows pushed through prefill together (workspace sizing) */
+    int max_cond;        /* largest L_cond accepted */
+    int keep_history;    /* 1: store masked logits of every sub-step (B,steps,V) x2 like the reference */
+} sfb200_ar_config;
+
+/* weight tensor ids for sfb200_ar_weight_offset (names = the reference state_dict keys) */
+enum {
+    SFB200_W_POS_EMB = 0,        /* pos_emb (block_size, d) */
+    SFB200_W_COND_POS_EMB,       /* cond_pos_emb (block_size, d) */
+    SFB200_W_TOK_EMB0,           /* tok_embs.0.weight (V0, d) */
+    SFB200_W_TOK_EMB1,           /* tok_embs.1.weight (V1, d) */
+    SFB200_W_EXTRA_EMB,          /* extra_tok_embs.0.weight (Ve, d) */
+    SFB200_W_HEAD_LN_W,          /* heads.g.0.weight (d)            [group] */
+    SFB200_W_HEAD_LN_B,          /* heads.g.0.bias (d)              [group] */
+    SFB200_W_HEAD_W,             /* heads.g.1.weight (V_g, d)       [group] */
+    SFB200_W_LN1_W,              /* blocks.g.l.ln1.weight           [group, layer] */
+    SFB200_W_LN1_B,
+    SFB200_W_QKV_W,              /* cat(attn.query, attn.key, attn.value).weight (3d, d) */
+    SFB200_W_QKV_B,              /* (3d) */
+    SFB200_W_PROJ_W,             /* attn.proj.weight (d, d) */
+    SFB200_W_PROJ_B,
+    SFB200_W_LN2_W,
+    SFB200_W_LN2_B,
+    SFB200_W_FC1_W,              /* mlp.0.weight (4d, d) */
+    SFB200_W_FC1_B,
+    SFB200_W_FC2_W,              /* mlp.2.weight (d, 4d) */
+    SFB200_W_FC2_B,
+    SFB200_W_COUNT
+};
+
+/* sizes (bytes unless stated) the caller must allocate */
+int64_t sfb200_ar_weight_floats(const sfb200_ar_config *cfg);
+int64_t sfb200_ar_weight_offset(const sfb200_ar_config *cfg, int tensor_id, int group, int layer); /* in floats, <0 = bad id */
+int64_t sfb200_ar_kv_bytes(const sfb200_ar_config *cfg);
+int64_t sfb200_ar_workspace_bytes(const sfb200_ar_config *cfg);
+int64_t sfb200_ar_history_floats(const sfb200_ar_config *cfg);  /* 0 when keep_history == 0 */
+
+typedef struct sfb200_ar sfb200_ar;  /* host-side handle (small, malloc'ed); owns no device memory */
+
+/* Bind caller-owned device buffers.  weights: packed per sfb200_ar_weight_offset.  tokens: (max_rows, max_len, 2) int64
+ * — the reference's `sampled` buffer (shapeformer/shapeformer.py:66-69).  history may be NULL iff keep_history == 0. */
+int sfb200_ar_create(const sfb200_ar_config *cfg, const float *weights, void *kv_cache, void *workspace, int64_t *tokens,
+                     float *history, sfb200_ar **out);
+void sfb200_ar_destroy(sfb200_ar *h);
+
+typedef struct sfb200_ar_sampling {
+    int top_k;                    /* <= 0 disables (common.py:265) */
+    float top_p;                  /* <= 0 disables (common.py:271) */
+    float temperature;
+    int best_in_first;            /* row 0 takes the greedy (top_k=1, top_p=0.001) draw (shapeformer.py:96-101) */
+    int mask_invalid;             /* representer attribute (representers.py:57,134) */
+    int mask_invalid_completion;  /* representer attribute (representers.py:141) */
+} sfb200_ar_sampling;
+
+/* Start a batch: B rows, each with L_cond conditioning tuples already written to tokens[:, :L_cond].  Runs the prefill:
+ * blocks[0] over positions [0, L_cond), blocks[1] over [0, L_cond-1), filling both KV caches, and leaves logits0 of the
+ * last conditioning position ready for step 0.  Replaces the first (and, being cached, every later) full forward of
+ * CondTupleGPT.sample_next_tuple (transformer/mingpt.py:297-310) and AR_N.get_extra_indices (representers.py:187-196). */
+int sfb200_ar_begin(sfb200_ar *h, int B, int L_cond, const sfb200_ar_sampling *sp, void *stream);
+
+/* Run `n_steps` AR steps (each = pos sub-pass + val sub-pass = one (pos,val) tuple per row), enqueued back to back.
+ * noise: (n_steps, 4, B, Vmax) fp32 Exp(1) draws in the reference's order per step: pos-sample, pos-best, val-sample,
+ * val-best (what torch.multinomial draws internally, shapeformer/common.py:296; Vmax = max(vocab)).
+ * use_graph != 0 captures one step into a CUDA graph and replays it.  Steps continue past "all rows ended"; the first
+ * step index at which every row's newest tuple holds an end token is recorded (sfb200_ar_status). */
+int sfb200_ar_steps(sfb200_ar *h, int n_steps, const float *noise, int use_graph, void *stream);
+
+/* Device-side status words the caller may copy back after a sync: status[0] = steps done, status[1] = first step index
+ * (0-based) at which all rows had ended, or -1.  Returns a device pointer to int32[4]. */
+const int32_t *sfb200_ar_status_ptr(const sfb200_ar *h);
+
+/* ---- individual AR operators (exposed for parity tests and profiling; the same kernels the calls above enqueue) ---- */
+
+/* y = act(x @ W^T + bias) + residual.  x (M,K), W (N,K), bias (N) or NULL, residual (M,N) or NULL (may alias y),
+ * act: 0 none, 1 exact-erf GELU (nn.GELU).  nn.Linear of mingpt.py:56-61,99-104,228. */
+int sfb200_linear(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
+                  int act, void *stream);
+
+/* LayerNorm over the last dim, eps = 1e-5 (mingpt.py:97-98,224). */
+int sfb200_layernorm(const float *x, const float *w, const float *b, float *y, int rows, int d, void *stream);
+
+/* Single-position causal attention with KV-cache append (CausalSelfAttention.forward mingpt.py:74-91, one new query).
+ * qkv (B, 3d): [q | k | v] of the new position; kcache / vcache (B, H, max_len, 64); the new k,v are written at index
+ * `pos` and the query attends to positions [0, pos].  pos is read from *pos_dev when pos_dev != NULL (graph replay).
+ * out (B, d).  part: workspace for split-KV partials (B*H*n_split*(64+2) floats) or NULL when n_split == 1. */
+int sfb200_attn_decode(const float *qkv, float *kcache, float *vcache, float *out, float *part, int B, int H, int max_len,
+                       int pos, const int32_t *pos_dev, int n_split, void *stream);
+
+/* Causal attention over T new positions (prefill) + KV-cache fill.  qkv (B, T, 3d); writes k,v to cache [0,T). out (B,T,d) */
+int sfb200_attn_prefill(const float *qkv, float *kcache, float *vcache, float *out, int B, int H, int T, int max_len,
+                        void *stream);
+
+/* sampling_masker + filter_sampling_logits + sample_logits for one tuple element (representers.py:120-155,
+ * common.py:260-299).  logits (B,V); tokens (B,max_len,2); writes tokens[b][L][tuple_i]; hist_out (B,V) masked logits
+ * or NULL.  noise_sample / noise_best (B,V).  L = current length (position being sampled), step_j = L - L_cond. */
+int sfb200_ar_sample(const float *logits, int64_t *tokens, float *hist_out, const float *noise_sample,
+                     const float *noise_best, int B, int V, int max_len, int L, int L_cond, int tuple_i,
+                     const int64_t *end_tokens, const sfb200_ar_sampling *sp, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFB200_H */

@@ -1,0 +1,120 @@
+"""ctypes binding of libsfb200.so (include/sfb200.h).  There is no CPU or PyTorch fallback: if the library is missing or
+a call fails, this module raises."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsfb200.so")
+
+c_i64p = ctypes.POINTER(ctypes.c_int64)
+c_f32p = ctypes.POINTER(ctypes.c_float)
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+vp = ctypes.c_void_p
+
+
+class ArConfig(ctypes.Structure):
+    """struct sfb200_ar_config"""
+    _fields_ = [
+        ("n_embd", ctypes.c_int), ("n_head", ctypes.c_int), ("n_layers", ctypes.c_int * 2),
+        ("block_size", ctypes.c_int), ("vocab", ctypes.c_int * 2), ("extra_vocab", ctypes.c_int),
+        ("end_tokens", ctypes.c_int64 * 2),
+        ("max_rows", ctypes.c_int), ("max_len", ctypes.c_int), ("max_steps", ctypes.c_int),
+        ("prefill_rows", ctypes.c_int), ("max_cond", ctypes.c_int), ("keep_history", ctypes.c_int),
+    ]
+
+
+class ArSampling(ctypes.Structure):
+    """struct sfb200_ar_sampling"""
+    _fields_ = [
+        ("top_k", ctypes.c_int), ("top_p", ctypes.c_float), ("temperature", ctypes.c_float),
+        ("best_in_first", ctypes.c_int), ("mask_invalid", ctypes.c_int), ("mask_invalid_completion", ctypes.c_int),
+    ]
+
+
+# tensor ids of sfb200_ar_weight_offset
+(W_POS_EMB, W_COND_POS_EMB, W_TOK_EMB0, W_TOK_EMB1, W_EXTRA_EMB, W_HEAD_LN_W, W_HEAD_LN_B, W_HEAD_W, W_LN1_W, W_LN1_B,
+ W_QKV_W, W_QKV_B, W_PROJ_W, W_PROJ_B, W_LN2_W, W_LN2_B, W_FC1_W, W_FC1_B, W_FC2_W, W_FC2_B, W_COUNT) = range(21)
+
+DEC_MLP_FLOATS = 32 * 3 + 32 + 5 * (3 * (32 * 32 + 32)) + 32 + 1
+
+# name -> (restype, argtypes); mirrors include/sfb200.h one to one (tests/test_cabi.py checks the export list)
+SIGNATURES = {
+    "sfb200_version": (ctypes.c_int, []),
+    "sfb200_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "sfb200_last_cuda_error": (ctypes.c_char_p, []),
+    "sfb200_code_gather": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
+    "sfb200_grid_to_channels_last": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int64, vp]),
+    "sfb200_decoder_set_weights": (ctypes.c_int, [vp, vp]),
+    "sfb200_decoder_points": (ctypes.c_int, [vp, vp, ctypes.c_int64, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int64,
+                                             ctypes.c_int, vp]),
+    "sfb200_tokens_to_dense": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64,
+                                              ctypes.c_int64, vp]),
+    "sfb200_ar_weight_floats": (ctypes.c_int64, [ctypes.POINTER(ArConfig)]),
+    "sfb200_ar_weight_offset": (ctypes.c_int64, [ctypes.POINTER(ArConfig), ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "sfb200_ar_kv_bytes": (ctypes.c_int64, [ctypes.POINTER(ArConfig)]),
+    "sfb200_ar_workspace_bytes": (ctypes.c_int64, [ctypes.POINTER(ArConfig)]),
+    "sfb200_ar_history_floats": (ctypes.c_int64, [ctypes.POINTER(ArConfig)]),
+    "sfb200_ar_create": (ctypes.c_int, [ctypes.POINTER(ArConfig), vp, vp, vp, vp, vp, ctypes.POINTER(vp)]),
+    "sfb200_ar_destroy": (None, [vp]),
+    "sfb200_ar_begin": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ArSampling), vp]),
+    "sfb200_ar_steps": (ctypes.c_int, [vp, ctypes.c_int, vp, ctypes.c_int, vp]),
+    "sfb200_ar_status_ptr": (vp, [vp]),
+    "sfb200_linear": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
+    "sfb200_layernorm": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp]),
+    "sfb200_attn_decode": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,
+                                          ctypes.c_int, vp]),
+    "sfb200_attn_prefill": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
+    "sfb200_ar_sample": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(ArSampling), vp]),
+}
+
+
+class Sfb200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libsfb200.so (once).  Raises if it has not been built — there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Sfb200Error(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          f"(or ./build.sh). shapeformer_b200 has no CPU/PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.sfb200_version() != 100:
+        raise Sfb200Error(f"libsfb200 version mismatch: {lib.sfb200_version()}")
+    _lib = lib
+    return lib
+
+
+def check(code, what=""):
+    if code != 0:
+        lib = load()
+        msg = lib.sfb200_error_string(code).decode()
+        if code == -2:
+            msg += ": " + lib.sfb200_last_cuda_error().decode()
+        raise Sfb200Error(f"{what} failed: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL).  The tensor must be contiguous and on a CUDA device."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise Sfb200Error("libsfb200 takes device pointers only: got a CPU tensor (no CPU fallback exists)")
+    if not t.is_contiguous():
+        raise Sfb200Error("tensor must be contiguous")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,355 @@
+// Host-side engine of the AR sampler: packed-weight layout, workspace carving, prefill, and the per-step kernel sequence
+// (optionally replayed as a CUDA graph).  Replaces, for the hot path, the Python loop of ShapeFormer.sample_indices
+// (shapeformer/shapeformer.py:72-115) and the uncached CondTupleGPT.sample_next_tuple (transformer/mingpt.py:297-310).
+#include <stdlib.h>
+#include <string.h>
+
+#include "ar_kernels.cuh"
+
+namespace sfb {
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct Layout {
+    int d, H, V[2], Ve, bs, nl[2];
+    int64_t off[SFB200_W_COUNT];   // base offset of the first instance
+    int64_t per_layer;             // floats per transformer block
+    int64_t layer_base[2];         // offset of block (g, 0)
+    int64_t head_base[2];
+    int64_t total;
+};
+
+static int make_layout(const sfb200_ar_config *c, Layout *L) {
+    if (!c) return SFB200_E_ARG;
+    if (c->n_embd <= 0 || c->n_embd % 64 != 0 || c->n_head <= 0 || c->n_embd != c->n_head * 64) return SFB200_E_ARG;
+    if (c->n_layers[0] < 1 || c->n_layers[1] < 1 || c->block_size < 2) return SFB200_E_ARG;
+    if (c->vocab[0] < 2 || c->vocab[1] < 2 || c->vocab[0] > 8192 || c->vocab[1] > 8192 || c->extra_vocab < 1)
+        return SFB200_E_ARG;
+    L->d = c->n_embd; L->H = c->n_head; L->V[0] = c->vocab[0]; L->V[1] = c->vocab[1]; L->Ve = c->extra_vocab;
+    L->bs = c->block_size; L->nl[0] = c->n_layers[0]; L->nl[1] = c->n_layers[1];
+    const int64_t d = L->d;
+    int64_t o = 0;
+    L->off[SFB200_W_POS_EMB] = o; o += (int64_t)L->bs * d;
+    L->off[SFB200_W_COND_POS_EMB] = o; o += (int64_t)L->bs * d;
+    L->off[SFB200_W_TOK_EMB0] = o; o += (int64_t)L->V[0] * d;
+    L->off[SFB200_W_TOK_EMB1] = o; o += (int64_t)L->V[1] * d;
+    L->off[SFB200_W_EXTRA_EMB] = o; o += (int64_t)L->Ve * d;
+    for (int g = 0; g < 2; ++g) {
+        L->head_base[g] = o;
+        o += 2 * d + (int64_t)L->V[g] * d;
+    }
+    // within a block
+    int64_t p = 0;
+    L->off[SFB200_W_LN1_W] = p; p += d;
+    L->off[SFB200_W_LN1_B] = p; p += d;
+    L->off[SFB200_W_QKV_W] = p; p += 3 * d * d;
+    L->off[SFB200_W_QKV_B] = p; p += 3 * d;
+    L->off[SFB200_W_PROJ_W] = p; p += d * d;
+    L->off[SFB200_W_PROJ_B] = p; p += d;
+    L->off[SFB200_W_LN2_W] = p; p += d;
+    L->off[SFB200_W_LN2_B] = p; p += d;
+    L->off[SFB200_W_FC1_W] = p; p += 4 * d * d;
+    L->off[SFB200_W_FC1_B] = p; p += 4 * d;
+    L->off[SFB200_W_FC2_W] = p; p += 4 * d * d;
+    L->off[SFB200_W_FC2_B] = p; p += d;
+    L->per_layer = p;
+    L->layer_base[0] = o; o += p * L->nl[0];
+    L->layer_base[1] = o; o += p * L->nl[1];
+    L->total = o;
+    return SFB200_OK;
+}
+
+static int64_t weight_offset(const Layout *L, int id, int g, int l) {
+    if (id < 0 || id >= SFB200_W_COUNT) return -1;
+    if (id <= SFB200_W_EXTRA_EMB) return L->off[id];
+    if (g < 0 || g > 1) return -1;
+    if (id == SFB200_W_HEAD_LN_W) return L->head_base[g];
+    if (id == SFB200_W_HEAD_LN_B) return L->head_base[g] + L->d;
+    if (id == SFB200_W_HEAD_W) return L->head_base[g] + 2 * L->d;
+    if (l < 0 || l >= L->nl[g]) return -1;
+    return L->layer_base[g] + (int64_t)l * L->per_layer + L->off[id];
+}
+
+struct Buffers {   // byte offsets into the workspace
+    int64_t st, x0, x1, h, qkv, att, ff, logits[2], part;
+    int64_t px, px1, ph, pqkv, pff;
+    int64_t total;
+};
+
+static int pick_nsplit(int B, int H) {
+    int n = (2 * 148 + B * H - 1) / (B * H);
+    if (n < 1) n = 1;
+    if (n > 8) n = 8;
+    return n;
+}
+
+static void carve(const sfb200_ar_config *c, Buffers *b) {
+    const int64_t d = c->n_embd, B = c->max_rows, F = sizeof(float);
+    const int64_t Vmax = c->vocab[0] > c->vocab[1] ? c->vocab[0] : c->vocab[1];
+    const int64_t P = (int64_t)c->prefill_rows * c->max_cond;
+    int64_t o = 0;
+    auto take = [&](int64_t bytes) { int64_t r = o; o = align_up(o + bytes, 256); return r; };
+    b->st = take(ST_WORDS * 4);
+    b->x0 = take(B * d * F);
+    b->x1 = take(B * d * F);
+    b->h = take(B * d * F);
+    b->qkv = take(B * 3 * d * F);
+    b->att = take(B * d * F);
+    b->ff = take(B * 4 * d * F);
+    b->logits[0] = take(B * Vmax * F);
+    b->logits[1] = take(B * Vmax * F);
+    b->part = take(B * c->n_head * 8 * 66 * F);
+    b->px = take(P * d * F);
+    b->px1 = take(P * d * F);
+    b->ph = take(P * d * F);
+    b->pqkv = take(P * 3 * d * F);
+    b->pff = take(P * 4 * d * F);
+    b->total = o;
+}
+
+}  // namespace sfb
+
+using namespace sfb;
+
+struct sfb200_ar {
+    sfb200_ar_config cfg;
+    Layout lay;
+    Buffers buf;
+    const float *w;
+    char *ws;
+    float *kv;
+    int64_t *tokens;
+    float *hist;
+    int Vmax;
+    // per batch
+    int B, L_cond, n_split;
+    bool begun;
+    sfb200_ar_sampling sp;
+    // graph
+    cudaGraphExec_t gexec;
+    const float *g_noise;
+    int g_B;
+    sfb200_ar_sampling g_sp;
+};
+
+static inline const float *W_(const sfb200_ar *h, int id, int g, int l) { return h->w + weight_offset(&h->lay, id, g, l); }
+template <typename T>
+static inline T *WS_(const sfb200_ar *h, int64_t off) { return reinterpret_cast<T *>(h->ws + off); }
+
+// K cache of block (g, l): (max_rows, H, max_len, 64); V cache follows K.
+static inline float *kcache(const sfb200_ar *h, int g, int l, int row0) {
+    const int64_t per = (int64_t)h->cfg.max_rows * h->cfg.n_head * h->cfg.max_len * 64;
+    const int64_t li = (g == 0 ? 0 : h->cfg.n_layers[0]) + l;
+    return h->kv + li * 2 * per + (int64_t)row0 * h->cfg.n_head * h->cfg.max_len * 64;
+}
+static inline float *vcache(const sfb200_ar *h, int g, int l, int row0) {
+    const int64_t per = (int64_t)h->cfg.max_rows * h->cfg.n_head * h->cfg.max_len * 64;
+    return kcache(h, g, l, row0) + per;
+}
+
+extern "C" {
+
+int64_t sfb200_ar_weight_floats(const sfb200_ar_config *cfg) {
+    Layout L;
+    if (make_layout(cfg, &L) != SFB200_OK) return -1;
+    return L.total;
+}
+int64_t sfb200_ar_weight_offset(const sfb200_ar_config *cfg, int tensor_id, int group, int layer) {
+    Layout L;
+    if (make_layout(cfg, &L) != SFB200_OK) return -1;
+    return weight_offset(&L, tensor_id, group, layer);
+}
+int64_t sfb200_ar_kv_bytes(const sfb200_ar_config *cfg) {
+    if (!cfg) return -1;
+    return (int64_t)(cfg->n_layers[0] + cfg->n_layers[1]) * 2 * cfg->max_rows * cfg->n_head * cfg->max_len * 64 * 4;
+}
+int64_t sfb200_ar_workspace_bytes(const sfb200_ar_config *cfg) {
+    if (!cfg) return -1;
+    Buffers b;
+    carve(cfg, &b);
+    return b.total;
+}
+int64_t sfb200_ar_history_floats(const sfb200_ar_config *cfg) {
+    if (!cfg) return -1;
+    if (!cfg->keep_history) return 0;
+    return (int64_t)cfg->max_rows * cfg->max_steps * ((int64_t)cfg->vocab[0] + cfg->vocab[1]);
+}
+
+int sfb200_ar_create(const sfb200_ar_config *cfg, const float *weights, void *kv_cache, void *workspace, int64_t *tokens,
+                     float *history, sfb200_ar **out) {
+    if (!cfg || !weights || !kv_cache || !workspace || !tokens || !out) return SFB200_E_ARG;
+    if (cfg->keep_history && !history) return SFB200_E_ARG;
+    if (cfg->max_rows < 1 || cfg->max_len < 2 || cfg->max_steps < 1 || cfg->prefill_rows < 1 || cfg->max_cond < 1)
+        return SFB200_E_ARG;
+    if (cfg->max_len > cfg->block_size || cfg->max_cond >= cfg->max_len || cfg->prefill_rows > cfg->max_rows)
+        return SFB200_E_ARG;
+    sfb200_ar *h = static_cast<sfb200_ar *>(calloc(1, sizeof(sfb200_ar)));
+    if (!h) return SFB200_E_ARG;
+    h->cfg = *cfg;
+    int r = make_layout(cfg, &h->lay);
+    if (r != SFB200_OK) { free(h); return r; }
+    carve(cfg, &h->buf);
+    h->w = weights;
+    h->ws = static_cast<char *>(workspace);
+    h->kv = static_cast<float *>(kv_cache);
+    h->tokens = tokens;
+    h->hist = cfg->keep_history ? history : nullptr;
+    h->Vmax = cfg->vocab[0] > cfg->vocab[1] ? cfg->vocab[0] : cfg->vocab[1];
+    h->begun = false;
+    h->gexec = nullptr;
+    *out = h;
+    return SFB200_OK;
+}
+
+void sfb200_ar_destroy(sfb200_ar *h) {
+    if (!h) return;
+    if (h->gexec) cudaGraphExecDestroy(h->gexec);
+    free(h);
+}
+
+const int32_t *sfb200_ar_status_ptr(const sfb200_ar *h) { return h ? WS_<int32_t>(h, h->buf.st) : nullptr; }
+
+}  // extern "C"
+
+// One transformer block over M = rows*T positions (prefill) — Block.forward, transformer/mingpt.py:108-111.
+static int block_prefill(sfb200_ar *h, int g, int l, float *x, int row0, int rows, int T, cudaStream_t s) {
+    const int d = h->cfg.n_embd, H = h->cfg.n_head, M = rows * T;
+    float *ph = WS_<float>(h, h->buf.ph), *pqkv = WS_<float>(h, h->buf.pqkv), *pff = WS_<float>(h, h->buf.pff);
+    SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN1_W, g, l), W_(h, SFB200_W_LN1_B, g, l), ph, M, d, s));
+    SFB_TRY(launch_linear(ph, W_(h, SFB200_W_QKV_W, g, l), W_(h, SFB200_W_QKV_B, g, l), nullptr, pqkv, M, 3 * d, d, 0, s));
+    SFB_TRY(launch_attn_prefill(pqkv, kcache(h, g, l, row0), vcache(h, g, l, row0), ph, rows, H, T, h->cfg.max_len, s));
+    SFB_TRY(launch_linear(ph, W_(h, SFB200_W_PROJ_W, g, l), W_(h, SFB200_W_PROJ_B, g, l), x, x, M, d, d, 0, s));
+    SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN2_W, g, l), W_(h, SFB200_W_LN2_B, g, l), ph, M, d, s));
+    SFB_TRY(launch_linear(ph, W_(h, SFB200_W_FC1_W, g, l), W_(h, SFB200_W_FC1_B, g, l), nullptr, pff, M, 4 * d, d, 1, s));
+    SFB_TRY(launch_linear(pff, W_(h, SFB200_W_FC2_W, g, l), W_(h, SFB200_W_FC2_B, g, l), x, x, M, d, 4 * d, 0, s));
+    return SFB200_OK;
+}
+
+// One transformer block for the newest position of every row (decode), position read from the device state.
+static int block_step(sfb200_ar *h, int g, int l, float *x, cudaStream_t s) {
+    const int d = h->cfg.n_embd, H = h->cfg.n_head, B = h->B;
+    const int32_t *st = WS_<int32_t>(h, h->buf.st);
+    float *hb = WS_<float>(h, h->buf.h), *qkv = WS_<float>(h, h->buf.qkv), *att = WS_<float>(h, h->buf.att);
+    float *ff = WS_<float>(h, h->buf.ff), *part = WS_<float>(h, h->buf.part);
+    SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN1_W, g, l), W_(h, SFB200_W_LN1_B, g, l), hb, B, d, s));
+    SFB_TRY(launch_linear(hb, W_(h, SFB200_W_QKV_W, g, l), W_(h, SFB200_W_QKV_B, g, l), nullptr, qkv, B, 3 * d, d, 0, s));
+    SFB_TRY(launch_attn_decode(qkv, kcache(h, g, l, 0), vcache(h, g, l, 0), att, part, B, H, h->cfg.max_len, 0, st,
+                               h->n_split, s));
+    SFB_TRY(launch_linear(att, W_(h, SFB200_W_PROJ_W, g, l), W_(h, SFB200_W_PROJ_B, g, l), x, x, B, d, d, 0, s));
+    SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN2_W, g, l), W_(h, SFB200_W_LN2_B, g, l), hb, B, d, s));
+    SFB_TRY(launch_linear(hb, W_(h, SFB200_W_FC1_W, g, l), W_(h, SFB200_W_FC1_B, g, l), nullptr, ff, B, 4 * d, d, 1, s));
+    SFB_TRY(launch_linear(ff, W_(h, SFB200_W_FC2_W, g, l), W_(h, SFB200_W_FC2_B, g, l), x, x, B, d, 4 * d, 0, s));
+    return SFB200_OK;
+}
+
+static int head(sfb200_ar *h, int g, const float *x, float *logits, int rows, cudaStream_t s) {
+    const int d = h->cfg.n_embd;
+    float *hb = WS_<float>(h, h->buf.h);
+    SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_HEAD_LN_W, g, 0), W_(h, SFB200_W_HEAD_LN_B, g, 0), hb, rows, d, s));
+    SFB_TRY(launch_linear(hb, W_(h, SFB200_W_HEAD_W, g, 0), nullptr, nullptr, logits, rows, h->cfg.vocab[g], d, 0, s));
+    return SFB200_OK;
+}
+
+extern "C" int sfb200_ar_begin(sfb200_ar *h, int B, int L_cond, const sfb200_ar_sampling *sp, void *stream) {
+    if (!h || !sp) return SFB200_E_ARG;
+    if (B < 1 || B > h->cfg.max_rows || L_cond < 1 || L_cond > h->cfg.max_cond) return SFB200_E_ARG;
+    if (!(sp->temperature > 0.f)) return SFB200_E_ARG;
+    cudaStream_t s = as_stream(stream);
+    const int d = h->cfg.n_embd;
+    h->B = B; h->L_cond = L_cond; h->sp = *sp;
+    h->n_split = pick_nsplit(B, h->cfg.n_head);
+    int32_t *st = WS_<int32_t>(h, h->buf.st);
+    SFB_TRY(launch_state_init(st, L_cond, s));
+    float *px = WS_<float>(h, h->buf.px), *px1 = WS_<float>(h, h->buf.px1), *x0 = WS_<float>(h, h->buf.x0);
+    const int64_t end0 = h->cfg.end_tokens[0];
+    for (int r0 = 0; r0 < B; r0 += h->cfg.prefill_rows) {
+        const int rows = (B - r0 < h->cfg.prefill_rows) ? B - r0 : h->cfg.prefill_rows;
+        const int64_t *tok = h->tokens + (int64_t)r0 * h->cfg.max_len * 2;
+        SFB_TRY(launch_embed(tok, W_(h, SFB200_W_TOK_EMB0, 0, 0), W_(h, SFB200_W_TOK_EMB1, 0, 0),
+                             W_(h, SFB200_W_EXTRA_EMB, 0, 0), W_(h, SFB200_W_POS_EMB, 0, 0),
+                             W_(h, SFB200_W_COND_POS_EMB, 0, 0), px, rows, d, h->cfg.max_len, 0, L_cond, L_cond, end0,
+                             nullptr, s));
+        for (int l = 0; l < h->cfg.n_layers[0]; ++l) SFB_TRY(block_prefill(h, 0, l, px, r0, rows, L_cond, s));
+        SFB_TRY(launch_take_last(px, x0 + (int64_t)r0 * d, rows, d, L_cond, s));
+        const int T1 = L_cond - 1;
+        if (T1 > 0) {
+            // blocks[1] input of position t is blocks[0] output + tok_embs[0](pos of tuple t+1)   (mingpt.py:309)
+            SFB_TRY(launch_add_target(px, px1, tok, W_(h, SFB200_W_TOK_EMB0, 0, 0), rows, d, h->cfg.max_len, 0, T1, nullptr,
+                                      s, L_cond));
+            for (int l = 0; l < h->cfg.n_layers[1]; ++l) SFB_TRY(block_prefill(h, 1, l, px1, r0, rows, T1, s));
+        }
+    }
+    SFB_TRY(head(h, 0, x0, WS_<float>(h, h->buf.logits[0]), B, s));
+    h->begun = true;
+    return SFB200_OK;
+}
+
+// One AR step: sample pos -> blocks[1] + head[1] for position L-1 -> sample val -> L += 1 -> blocks[0] + head[0] for the
+// new position L-1 (so that logits0 is ready for the next step).
+static int enqueue_step(sfb200_ar *h, const float *noise, cudaStream_t s) {
+    const int d = h->cfg.n_embd, B = h->B;
+    int32_t *st = WS_<int32_t>(h, h->buf.st);
+    float *x0 = WS_<float>(h, h->buf.x0), *x1 = WS_<float>(h, h->buf.x1);
+    const int64_t draw = (int64_t)B * h->Vmax;
+    SampleLaunch p;
+    p.tokens = h->tokens; p.B = B; p.max_len = h->cfg.max_len; p.L = 0; p.L_cond = 0;
+    p.end0 = h->cfg.end_tokens[0]; p.end1 = h->cfg.end_tokens[1]; p.sp = h->sp; p.st = st;
+    p.noise_step_stride = 4 * draw; p.noise_row_stride = h->Vmax;
+    // --- position
+    p.logits = WS_<float>(h, h->buf.logits[0]); p.V = h->cfg.vocab[0]; p.tuple_i = 0;
+    p.hist = h->hist; p.hist_row_stride = (int64_t)h->cfg.max_steps * h->cfg.vocab[0];
+    p.noise_sample = noise; p.noise_best = noise + draw;
+    SFB_TRY(launch_sample(p, s));
+    // --- value
+    SFB_TRY(launch_add_target(x0, x1, h->tokens, W_(h, SFB200_W_TOK_EMB0, 0, 0), B, d, h->cfg.max_len, 0, 1, st, s, 1));
+    for (int l = 0; l < h->cfg.n_layers[1]; ++l) SFB_TRY(block_step(h, 1, l, x1, s));
+    SFB_TRY(head(h, 1, x1, WS_<float>(h, h->buf.logits[1]), B, s));
+    p.logits = WS_<float>(h, h->buf.logits[1]); p.V = h->cfg.vocab[1]; p.tuple_i = 1;
+    p.hist = h->hist ? h->hist + (int64_t)h->cfg.max_rows * h->cfg.max_steps * h->cfg.vocab[0] : nullptr;
+    p.hist_row_stride = (int64_t)h->cfg.max_steps * h->cfg.vocab[1];
+    p.noise_sample = noise + 2 * draw; p.noise_best = noise + 3 * draw;
+    SFB_TRY(launch_sample(p, s));
+    SFB_TRY(launch_advance(st, h->tokens, B, h->cfg.max_len, p.end0, p.end1, s));
+    // --- next position through blocks[0]
+    SFB_TRY(launch_embed(h->tokens, W_(h, SFB200_W_TOK_EMB0, 0, 0), W_(h, SFB200_W_TOK_EMB1, 0, 0),
+                         W_(h, SFB200_W_EXTRA_EMB, 0, 0), W_(h, SFB200_W_POS_EMB, 0, 0), W_(h, SFB200_W_COND_POS_EMB, 0, 0),
+                         x0, B, d, h->cfg.max_len, 0, 1, 0, p.end0, st, s));
+    for (int l = 0; l < h->cfg.n_layers[0]; ++l) SFB_TRY(block_step(h, 0, l, x0, s));
+    SFB_TRY(head(h, 0, x0, WS_<float>(h, h->buf.logits[0]), B, s));
+    return SFB200_OK;
+}
+
+static bool same_sp(const sfb200_ar_sampling &a, const sfb200_ar_sampling &b) { return memcmp(&a, &b, sizeof(a)) == 0; }
+
+extern "C" int sfb200_ar_steps(sfb200_ar *h, int n_steps, const float *noise, int use_graph, void *stream) {
+    if (!h || !noise || n_steps < 0) return SFB200_E_ARG;
+    if (!h->begun) return SFB200_E_STATE;
+    cudaStream_t s = as_stream(stream);
+    int32_t *st = WS_<int32_t>(h, h->buf.st);
+    SFB_TRY(launch_chunk_reset(st, s));
+    int done = 0;
+    if (use_graph) {
+        const bool valid = h->gexec && h->g_noise == noise && h->g_B == h->B && same_sp(h->g_sp, h->sp);
+        if (!valid) {
+            if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+            if (n_steps > 0) {   // first step eagerly: loads modules and sets function attributes outside capture
+                SFB_TRY(enqueue_step(h, noise, s));
+                done = 1;
+            }
+            cudaGraph_t graph = nullptr;
+            SFB_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            const int r = enqueue_step(h, noise, s);
+            const cudaError_t e = cudaStreamEndCapture(s, &graph);
+            if (r != SFB200_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+            SFB_CUDA_TRY(e);
+            const cudaError_t ei = cudaGraphInstantiate(&h->gexec, graph, 0);
+            cudaGraphDestroy(graph);
+            SFB_CUDA_TRY(ei);
+            h->g_noise = noise; h->g_B = h->B; h->g_sp = h->sp;
+        }
+        for (; done < n_steps; ++done) SFB_CUDA_TRY(cudaGraphLaunch(h->gexec, s));
+    } else {
+        for (; done < n_steps; ++done) SFB_TRY(enqueue_step(h, noise, s));
+    }
+    return SFB200_OK;
+}

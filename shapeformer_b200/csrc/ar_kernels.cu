@@ -1,0 +1,865 @@
+// AR sampler kernels: embed (+ AR_N extra index), LayerNorm, skinny/tiled fp32 GEMM with cluster split-K, single-query
+// attention with KV-cache append, causal prefill attention, and the mask -> filter -> sample kernel.
+//
+// Arithmetic is fp32 throughout with fp32 accumulation: sampled tokens must equal the reference's for a given noise
+// tensor, which needs logits within ~1e-5 of the fp32 PyTorch path.
+#include <cooperative_groups.h>
+
+#include "ar_kernels.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace sfb {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// device state words (int32), shared by all step kernels so that a captured CUDA graph is step-invariant
+// ---------------------------------------------------------------------------------------------------------------------
+//   st[ST_STEPS]  steps completed so far in this batch (the reference's loop variable j)
+//   st[ST_ENDED]  first step index at which every row's newest tuple held an end token, or -1
+//   st[ST_LEN]    current sequence length L (the position being sampled); newest complete tuple is L-1
+//   st[ST_LCOND]  L_cond
+//   st[ST_CHUNK]  step index inside the current sfb200_ar_steps call (selects the noise slab)
+
+__global__ void ar_state_init_kernel(int32_t *st, int L_cond) {
+    if (threadIdx.x == 0) {
+        st[ST_STEPS] = 0;
+        st[ST_ENDED] = -1;
+        st[ST_LEN] = L_cond;
+        st[ST_LCOND] = L_cond;
+        st[ST_CHUNK] = 0;
+    }
+}
+__global__ void ar_chunk_reset_kernel(int32_t *st) {
+    if (threadIdx.x == 0) st[ST_CHUNK] = 0;
+}
+
+// After the val sub-pass: end detection (shapeformer.py:110-115) and L += 1.
+__global__ void ar_advance_kernel(int32_t *st, const int64_t *tokens, int B, int max_len, int64_t end0, int64_t end1) {
+    __shared__ int not_ended;
+    if (threadIdx.x == 0) not_ended = 0;
+    __syncthreads();
+    const int L = st[ST_LEN];
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const int64_t *t = tokens + ((size_t)b * max_len + L) * 2;
+        if (t[0] != end0 && t[1] != end1) atomicAdd(&not_ended, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (not_ended == 0 && st[ST_ENDED] < 0) st[ST_ENDED] = st[ST_STEPS];
+        st[ST_STEPS] += 1;
+        st[ST_LEN] = L + 1;
+        st[ST_CHUNK] += 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Embedding: tok_embs[0](pos) + tok_embs[1](val) + extra_tok_embs[0](extra) + positional row, with AR_N's extra index
+// (transformer/mingpt.py:256-286, representers.py:187-196,432-442) computed in place.
+// One CTA per (row, position).  T positions starting at t0 (t0 read from st[ST_LEN]-1 when st != NULL).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ar_embed_kernel(const int64_t *__restrict__ tokens, const float *__restrict__ emb0,
+                                                       const float *__restrict__ emb1, const float *__restrict__ embx,
+                                                       const float *__restrict__ pos_emb,
+                                                       const float *__restrict__ cond_pos_emb, float *__restrict__ x,
+                                                       int d, int max_len, int t0_arg, int T, int L_cond_arg,
+                                                       int64_t end0, const int32_t *__restrict__ st) {
+    const int b = blockIdx.y;
+    const int t0 = st ? st[ST_LEN] - 1 : t0_arg;
+    const int L_cond = st ? st[ST_LCOND] : L_cond_arg;
+    const int t = t0 + blockIdx.x;
+    const int64_t *row = tokens + (size_t)b * max_len * 2;
+    const int64_t pos = row[2 * t], val = row[2 * t + 1];
+    int64_t extra;
+    if (t < L_cond) {
+        extra = pos;
+    } else if (pos == end0) {
+        extra = end0;
+    } else {
+        // searchsorted(c_pos, pos, right=True): first index with c_pos[idx] > pos
+        int lo = 0, hi = L_cond;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (row[2 * mid] > pos) hi = mid; else lo = mid + 1;
+        }
+        if (lo >= L_cond) lo = L_cond - 1;  // reference would raise in gather; conditioning always ends with end token
+        extra = row[2 * lo];
+    }
+    const float *e0 = emb0 + (size_t)pos * d, *e1 = emb1 + (size_t)val * d, *ex = embx + (size_t)extra * d;
+    const float *pe = (t < L_cond) ? cond_pos_emb + (size_t)t * d : pos_emb + (size_t)(t - L_cond) * d;
+    float *o = x + ((size_t)b * T + blockIdx.x) * d;
+    for (int i = threadIdx.x * 4; i < d; i += blockDim.x * 4) {
+        float4 a = ld4(e0 + i), c = ld4(e1 + i), e = ld4(ex + i), p = ld4(pe + i);
+        float4 r;
+        r.x = ((a.x + c.x) + e.x) + p.x;
+        r.y = ((a.y + c.y) + e.y) + p.y;
+        r.z = ((a.z + c.z) + e.z) + p.z;
+        r.w = ((a.w + c.w) + e.w) + p.w;
+        st4(o + i, r);
+    }
+}
+
+// x_out[b, i] = x_in[b, i] + emb0[tokens[b][t(b,i) + 1][0]]   ("x = x + tok_embs[0](target)", mingpt.py:309)
+// x_out rows are laid out (b, i) with i < T, x_in rows (b, i) with row stride Tin; source position t = t0 + i.
+__global__ void __launch_bounds__(256) ar_add_target_kernel(const float *__restrict__ x_in, float *__restrict__ x_out,
+                                                            const int64_t *__restrict__ tokens,
+                                                            const float *__restrict__ emb0, int d, int max_len, int t0_arg,
+                                                            int T, int Tin, const int32_t *__restrict__ st) {
+    const int b = blockIdx.y;
+    const int t0 = st ? st[ST_LEN] - 1 : t0_arg;
+    const int t = t0 + blockIdx.x;
+    const int64_t tgt = tokens[((size_t)b * max_len + t + 1) * 2];
+    const float *e = emb0 + (size_t)tgt * d;
+    const float *xi = x_in + ((size_t)b * Tin + blockIdx.x) * d;
+    float *xo = x_out + ((size_t)b * T + blockIdx.x) * d;
+    for (int i = threadIdx.x * 4; i < d; i += blockDim.x * 4) {
+        float4 a = ld4(xi + i), c = ld4(e + i);
+        a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+        st4(xo + i, a);
+    }
+}
+
+// out[b, :] = x[b, T-1, :]
+__global__ void ar_take_last_kernel(const float *__restrict__ x, float *__restrict__ out, int d, int T) {
+    const int b = blockIdx.x;
+    const float *s = x + ((size_t)b * T + (T - 1)) * d;
+    float *o = out + (size_t)b * d;
+    for (int i = threadIdx.x * 4; i < d; i += blockDim.x * 4) st4(o + i, ld4(s + i));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// LayerNorm (eps 1e-5, biased variance), one warp per row.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                        const float *__restrict__ bvec, float *__restrict__ y, int rows,
+                                                        int d) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const float *xr = x + (size_t)warp * d;
+    float *yr = y + (size_t)warp * d;
+    float s = 0.f;
+    for (int i = lane * 4; i < d; i += 128) {
+        float4 v = ld4(xr + i);
+        s += (v.x + v.y) + (v.z + v.w);
+    }
+    const float mean = warp_sum(s) / (float)d;
+    float q = 0.f;
+    for (int i = lane * 4; i < d; i += 128) {
+        float4 v = ld4(xr + i);
+        float a = v.x - mean, b = v.y - mean, c = v.z - mean, e = v.w - mean;
+        q += (a * a + b * b) + (c * c + e * e);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)d + 1e-5f);
+    for (int i = lane * 4; i < d; i += 128) {
+        float4 v = ld4(xr + i), g = ld4(w + i), bb = ld4(bvec + i), r;
+        r.x = (v.x - mean) * rstd * g.x + bb.x;
+        r.y = (v.y - mean) * rstd * g.y + bb.y;
+        r.z = (v.z - mean) * rstd * g.z + bb.z;
+        r.w = (v.w - mean) * rstd * g.w + bb.w;
+        st4(yr + i, r);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Linear: y = act(x W^T + bias) + residual, fp32 FFMA.
+// CTA tile (16*MI rows) x 64 cols, K streamed in 32-wide slabs through a 3-stage cp.async ring; both operands stay
+// K-major in shared memory (row stride 36 floats) and every thread reads float4 along K:
+//   thread (tn = tid & 15, tm = tid >> 4) owns outputs  m = tm + 16 i (i < MI),  n = tn + 16 j (j < 4).
+// Split-K runs as a thread-block cluster along z: partial tiles are exchanged through distributed shared memory and
+// summed in rank order (deterministic), then bias / GELU / residual are applied once.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int LIN_NT = 64, LIN_BK = 32, LIN_S = LIN_BK + 4, LIN_STAGES = 3;
+
+__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+
+template <int MI, int KSPLIT>
+__global__ void __launch_bounds__(256) linear_kernel(const float *__restrict__ x, const float *__restrict__ W,
+                                                     const float *__restrict__ bias, const float *residual, float *y,
+                                                     int M, int N, int K, int act) {
+    constexpr int MT = 16 * MI;
+    extern __shared__ __align__(16) float lin_smem[];
+    float *xs = lin_smem;                             // [STAGES][MT][S]
+    float *ws = lin_smem + LIN_STAGES * MT * LIN_S;   // [STAGES][NT][S]
+
+    const int tid = threadIdx.x, tn = tid & 15, tm = tid >> 4;
+    const int n0 = blockIdx.x * LIN_NT, m0 = blockIdx.y * MT;
+    const int kslice = K / KSPLIT;
+    const int kbeg = (KSPLIT > 1 ? (int)blockIdx.z : 0) * kslice;
+    const int nk = kslice / LIN_BK;
+
+    auto load_stage = [&](int stage, int kt) {
+        const int k0 = kbeg + kt * LIN_BK;
+        for (int i = tid; i < LIN_NT * 8; i += 256) {
+            const int r = i >> 3, c = i & 7, n = n0 + r;
+            const float *src = W + (size_t)(n < N ? n : N - 1) * K + k0 + c * 4;
+            cp_async16(ws + (stage * LIN_NT + r) * LIN_S + c * 4, src, n < N ? 16 : 0);
+        }
+        for (int i = tid; i < MT * 8; i += 256) {
+            const int r = i >> 3, c = i & 7, m = m0 + r;
+            const float *src = x + (size_t)(m < M ? m : M - 1) * K + k0 + c * 4;
+            cp_async16(xs + (stage * MT + r) * LIN_S + c * 4, src, m < M ? 16 : 0);
+        }
+    };
+
+    float acc[MI][4];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+#pragma unroll
+    for (int s = 0; s < LIN_STAGES - 1; ++s) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<LIN_STAGES - 2>();
+        __syncthreads();
+        if (kt + LIN_STAGES - 1 < nk) load_stage((kt + LIN_STAGES - 1) % LIN_STAGES, kt + LIN_STAGES - 1);
+        cp_async_commit();
+        const int stage = kt % LIN_STAGES;
+        const float *wst = ws + (stage * LIN_NT + tn) * LIN_S;
+        const float *xst = xs + (stage * MT + tm) * LIN_S;
+#pragma unroll
+        for (int k4 = 0; k4 < LIN_BK / 4; ++k4) {
+            float4 wv[4], xv[MI];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wv[j] = ld4(wst + 16 * j * LIN_S + k4 * 4);
+#pragma unroll
+            for (int i = 0; i < MI; ++i) xv[i] = ld4(xst + 16 * i * LIN_S + k4 * 4);
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float a = acc[i][j];
+                    a = fmaf(xv[i].x, wv[j].x, a);
+                    a = fmaf(xv[i].y, wv[j].y, a);
+                    a = fmaf(xv[i].z, wv[j].z, a);
+                    a = fmaf(xv[i].w, wv[j].w, a);
+                    acc[i][j] = a;
+                }
+        }
+    }
+    cp_async_wait<0>();
+
+    if (KSPLIT == 1) {
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            const int m = m0 + tm + 16 * i;
+            if (m >= M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + tn + 16 * j;
+                if (n >= N) continue;
+                float v = acc[i][j];
+                if (bias) v += bias[n];
+                if (act == 1) v = gelu_erf(v);
+                if (residual) v += residual[(size_t)m * N + n];
+                y[(size_t)m * N + n] = v;
+            }
+        }
+    } else {
+        cg::cluster_group cluster = cg::this_cluster();
+        __syncthreads();  // everyone is done with the operand ring; reuse it for the partial tile
+        float *red = lin_smem;  // [MT][64]
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) red[(tm + 16 * i) * LIN_NT + tn + 16 * j] = acc[i][j];
+        cluster.sync();
+        const unsigned rank = cluster.block_rank();
+        constexpr int CHUNK = MT * LIN_NT / KSPLIT;
+        const float *remote[KSPLIT];
+#pragma unroll
+        for (int r = 0; r < KSPLIT; ++r) remote[r] = cluster.map_shared_rank(red, r);
+        for (int e = tid; e < CHUNK; e += 256) {
+            const int idx = rank * CHUNK + e;
+            float v = 0.f;
+#pragma unroll
+            for (int r = 0; r < KSPLIT; ++r) v += remote[r][idx];
+            const int m = m0 + idx / LIN_NT, n = n0 + idx % LIN_NT;
+            if (m < M && n < N) {
+                if (bias) v += bias[n];
+                if (act == 1) v = gelu_erf(v);
+                if (residual) v += residual[(size_t)m * N + n];
+                y[(size_t)m * N + n] = v;
+            }
+        }
+        cluster.sync();  // keep shared memory alive until every peer has read it
+    }
+}
+
+template <int MI, int KSPLIT>
+static int launch_linear_t(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N,
+                           int K, int act, cudaStream_t stream) {
+    constexpr int MT = 16 * MI;
+    const size_t smem = (size_t)LIN_STAGES * (MT + LIN_NT) * LIN_S * sizeof(float);
+    static bool attr_done = false;  // per template instance
+    if (!attr_done) {
+        SFB_CUDA_TRY(cudaFuncSetAttribute(linear_kernel<MI, KSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((N + LIN_NT - 1) / LIN_NT, (M + MT - 1) / MT, KSPLIT);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = KSPLIT;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SFB_CUDA_TRY(cudaLaunchKernelEx(&cfg, linear_kernel<MI, KSPLIT>, x, W, bias, residual, y, M, N, K, act));
+    return SFB200_OK;
+}
+
+template <int MI>
+static int launch_linear_m(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N,
+                           int K, int act, int ksplit, cudaStream_t stream) {
+    switch (ksplit) {
+        case 1: return launch_linear_t<MI, 1>(x, W, bias, residual, y, M, N, K, act, stream);
+        case 2: return launch_linear_t<MI, 2>(x, W, bias, residual, y, M, N, K, act, stream);
+        case 4: return launch_linear_t<MI, 4>(x, W, bias, residual, y, M, N, K, act, stream);
+        case 8: return launch_linear_t<MI, 8>(x, W, bias, residual, y, M, N, K, act, stream);
+    }
+    return SFB200_E_ARG;
+}
+
+int pick_ksplit(int M, int N, int K, int MT) {
+    const int tiles = ((N + LIN_NT - 1) / LIN_NT) * ((M + MT - 1) / MT);
+    int ks = 1;
+    // grow the split while the grid is under ~2 CTAs per SM and every slice keeps >= 4 K-slabs
+    while (ks < 8 && tiles * ks < 2 * 148 && K % (ks * 2 * LIN_BK) == 0 && K / (ks * 2) >= 4 * LIN_BK) ks *= 2;
+    return ks;
+}
+
+int launch_linear(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
+                  int act, cudaStream_t stream) {
+    if (M <= 0 || N <= 0 || K <= 0 || K % LIN_BK != 0) return SFB200_E_ARG;
+    if (M <= 16) return launch_linear_m<1>(x, W, bias, residual, y, M, N, K, act, pick_ksplit(M, N, K, 16), stream);
+    if (M <= 32) return launch_linear_m<2>(x, W, bias, residual, y, M, N, K, act, pick_ksplit(M, N, K, 32), stream);
+    return launch_linear_m<4>(x, W, bias, residual, y, M, N, K, act, pick_ksplit(M, N, K, 64), stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Attention, one new query per (row, head), with KV-cache append.
+// CTA = 4 warps for one (b, h, split).  A half-warp owns one key at a time: lane c = lane & 15 holds dims 4c..4c+3 of
+// q / k / v, so one key row (256 B) is one coalesced 16-lane float4 load; each half-warp keeps its own online-softmax
+// state (m, l, acc[4]) and the 8 states are merged through shared memory at the end.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int ATT_U = 4;  // keys in flight per half-warp
+
+struct SoftState {
+    float m, l;
+    float4 acc;
+};
+
+__device__ __forceinline__ float half_warp_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+// Streams keys t = t_beg + g, t_beg + g + G, ... (< t_end) for key-group g of G; key t lives at kbase + t*kstride.
+__device__ __forceinline__ void attn_stream_keys(SoftState &st, const float4 q4, const float *__restrict__ kbase,
+                                                 const float *__restrict__ vbase, size_t kstride, int t_beg, int t_end,
+                                                 int g, int G, int c) {
+    for (int r0 = t_beg; r0 < t_end; r0 += G * ATT_U) {
+        float4 kk[ATT_U], vv[ATT_U];
+        bool ok[ATT_U];
+#pragma unroll
+        for (int u = 0; u < ATT_U; ++u) {
+            const int t = r0 + u * G + g;
+            ok[u] = t < t_end;
+            const size_t off = (size_t)(ok[u] ? t : t_beg) * kstride + c * 4;
+            kk[u] = ld4_stream(kbase + off);
+            vv[u] = ld4_stream(vbase + off);
+        }
+        float s[ATT_U];
+        float mx = st.m;
+#pragma unroll
+        for (int u = 0; u < ATT_U; ++u) {
+            float p = q4.x * kk[u].x;
+            p = fmaf(q4.y, kk[u].y, p);
+            p = fmaf(q4.z, kk[u].z, p);
+            p = fmaf(q4.w, kk[u].w, p);
+            p = half_warp_sum(p);
+            s[u] = ok[u] ? p : -INFINITY;
+            mx = fmaxf(mx, s[u]);
+        }
+        if (mx == -INFINITY) continue;
+        const float corr = expf(st.m - mx);  // st.m == -inf -> 0
+        st.l *= corr;
+        st.acc.x *= corr; st.acc.y *= corr; st.acc.z *= corr; st.acc.w *= corr;
+#pragma unroll
+        for (int u = 0; u < ATT_U; ++u) {
+            const float p = expf(s[u] - mx);  // -inf -> 0
+            st.l += p;
+            st.acc.x = fmaf(p, vv[u].x, st.acc.x);
+            st.acc.y = fmaf(p, vv[u].y, st.acc.y);
+            st.acc.z = fmaf(p, vv[u].z, st.acc.z);
+            st.acc.w = fmaf(p, vv[u].w, st.acc.w);
+        }
+        st.m = mx;
+    }
+}
+
+// Merge the per-half-warp states of one CTA (NG groups).  Result (unnormalised acc, M, Lsum) valid in warp 0, where
+// lane handles dims 2*lane, 2*lane+1.
+template <int NG>
+__device__ __forceinline__ void attn_merge(const SoftState &st, int grp, int c, float *sm /* NG*66 */, float &M,
+                                           float &Ls, float &o0, float &o1) {
+    float *mine = sm + grp * 66;
+    if (c == 0) { mine[64] = st.m; mine[65] = st.l; }
+    st4(mine + c * 4, st.acc);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        M = -INFINITY;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) M = fmaxf(M, sm[g * 66 + 64]);
+        Ls = 0.f; o0 = 0.f; o1 = 0.f;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const float mg = sm[g * 66 + 64];
+            const float w = (mg == -INFINITY) ? 0.f : expf(mg - M);
+            Ls = fmaf(sm[g * 66 + 65], w, Ls);
+            o0 = fmaf(sm[g * 66 + 2 * lane], w, o0);
+            o1 = fmaf(sm[g * 66 + 2 * lane + 1], w, o1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) attn_decode_kernel(const float *__restrict__ qkv, float *kcache, float *vcache,
+                                                          float *__restrict__ out, float *__restrict__ part, int H,
+                                                          int max_len, int pos_arg, const int32_t *__restrict__ st_dev,
+                                                          int n_split) {
+    __shared__ float sm[8 * 66];
+    const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z;
+    const int pos = st_dev ? st_dev[ST_LEN] - 1 : pos_arg;
+    const int d = H * 64;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = lane >> 4, c = lane & 15;
+    const int grp = warp * 2 + half;
+    const float *qrow = qkv + (size_t)b * 3 * d + h * 64 + c * 4;
+    float4 q4 = ld4(qrow);
+    q4.x *= 0.125f; q4.y *= 0.125f; q4.z *= 0.125f; q4.w *= 0.125f;  // 1/sqrt(64), exact
+    const size_t base = ((size_t)b * H + h) * (size_t)max_len * 64;
+
+    SoftState st;
+    st.m = -INFINITY; st.l = 0.f; st.acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sp == 0 && warp == 0) {
+        // the new position: append to the cache and seed group 0's state with it (no read-after-write).
+        // Both halves of warp 0 run the shuffle reduction (full-mask shuffles need all 32 lanes); only half 0 keeps it.
+        const float4 kn = ld4(qrow + d), vn = ld4(qrow + 2 * d);
+        float p = q4.x * kn.x;
+        p = fmaf(q4.y, kn.y, p); p = fmaf(q4.z, kn.z, p); p = fmaf(q4.w, kn.w, p);
+        p = half_warp_sum(p);
+        if (half == 0) {
+            st4(kcache + base + (size_t)pos * 64 + c * 4, kn);
+            st4(vcache + base + (size_t)pos * 64 + c * 4, vn);
+            st.m = p; st.l = 1.f; st.acc = vn;
+        }
+    }
+    // cached keys [0, pos) are divided between the splits in multiples of 8
+    int per = (pos + n_split - 1) / n_split;
+    per = (per + 7) & ~7;
+    const int t_beg = min(sp * per, pos), t_end = min(t_beg + per, pos);
+    attn_stream_keys(st, q4, kcache + base, vcache + base, 64, t_beg, t_end, grp, 8, c);
+
+    float M, Ls, o0, o1;
+    attn_merge<8>(st, grp, c, sm, M, Ls, o0, o1);
+    if (threadIdx.x < 32) {
+        if (n_split == 1) {
+            const float inv = 1.0f / Ls;
+            float2 r = make_float2(o0 * inv, o1 * inv);
+            *reinterpret_cast<float2 *>(out + (size_t)b * d + h * 64 + 2 * lane) = r;
+        } else {
+            float *p = part + (((size_t)b * H + h) * n_split + sp) * 66;
+            p[2 * lane] = o0; p[2 * lane + 1] = o1;
+            if (lane == 0) { p[64] = M; p[65] = Ls; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(64) attn_combine_kernel(const float *__restrict__ part, float *__restrict__ out, int H,
+                                                          int n_split) {
+    const int h = blockIdx.x, b = blockIdx.y, i = threadIdx.x;
+    const float *p = part + (((size_t)b * H + h) * n_split) * 66;
+    float M = -INFINITY;
+    for (int s = 0; s < n_split; ++s) M = fmaxf(M, p[s * 66 + 64]);
+    float Ls = 0.f, o = 0.f;
+    for (int s = 0; s < n_split; ++s) {
+        const float mg = p[s * 66 + 64];
+        const float w = (mg == -INFINITY) ? 0.f : expf(mg - M);
+        Ls = fmaf(p[s * 66 + 65], w, Ls);
+        o = fmaf(p[s * 66 + i], w, o);
+    }
+    out[(size_t)b * H * 64 + h * 64 + i] = o / Ls;
+}
+
+// Causal prefill: qkv (B, T, 3d).  CTA = 8 warps = 8 consecutive queries of one (b, h); each warp streams keys
+// [0, tq] straight from the qkv buffer (the 8 warps share them through L1) and scatters its own k, v into the cache.
+__global__ void __launch_bounds__(256) attn_prefill_kernel(const float *__restrict__ qkv, float *kcache, float *vcache,
+                                                           float *__restrict__ out, int H, int T, int max_len) {
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tq = blockIdx.z * 8 + warp;
+    if (tq >= T) return;
+    const int half = lane >> 4, c = lane & 15;
+    const int d = H * 64;
+    const size_t rs = (size_t)3 * d;  // stride between positions
+    const float *rowb = qkv + (size_t)b * T * rs + h * 64;
+    float4 q4 = ld4(rowb + (size_t)tq * rs + c * 4);
+    q4.x *= 0.125f; q4.y *= 0.125f; q4.z *= 0.125f; q4.w *= 0.125f;
+    if (half == 0) {
+        const size_t base = (((size_t)b * H + h) * (size_t)max_len + tq) * 64 + c * 4;
+        st4(kcache + base, ld4(rowb + (size_t)tq * rs + d + c * 4));
+        st4(vcache + base, ld4(rowb + (size_t)tq * rs + 2 * d + c * 4));
+    }
+    SoftState st;
+    st.m = -INFINITY; st.l = 0.f; st.acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    attn_stream_keys(st, q4, rowb + d, rowb + 2 * d, rs, 0, tq + 1, half, 2, c);
+    // merge the two halves of this warp
+    const float m2 = __shfl_xor_sync(0xffffffffu, st.m, 16), l2 = __shfl_xor_sync(0xffffffffu, st.l, 16);
+    float4 a2;
+    a2.x = __shfl_xor_sync(0xffffffffu, st.acc.x, 16);
+    a2.y = __shfl_xor_sync(0xffffffffu, st.acc.y, 16);
+    a2.z = __shfl_xor_sync(0xffffffffu, st.acc.z, 16);
+    a2.w = __shfl_xor_sync(0xffffffffu, st.acc.w, 16);
+    const float M = fmaxf(st.m, m2);
+    const float w1 = (st.m == -INFINITY) ? 0.f : expf(st.m - M), w2 = (m2 == -INFINITY) ? 0.f : expf(m2 - M);
+    // combine in a fixed (half 0, half 1) order on both halves so the two copies agree bitwise
+    const float wa = half ? w2 : w1, wb = half ? w1 : w2;
+    const float la = half ? l2 : st.l, lb = half ? st.l : l2;
+    const float4 xa = half ? a2 : st.acc, xb = half ? st.acc : a2;
+    const float Ls = fmaf(lb, wb, la * wa);
+    if (half == 0) {
+        const float inv = 1.0f / Ls;
+        float4 r;
+        r.x = fmaf(xb.x, wb, xa.x * wa) * inv;
+        r.y = fmaf(xb.y, wb, xa.y * wa) * inv;
+        r.z = fmaf(xb.z, wb, xa.z * wa) * inv;
+        r.w = fmaf(xb.w, wb, xa.w * wa) * inv;
+        st4(out + ((size_t)b * T + tq) * d + h * 64 + c * 4, r);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// mask -> temperature -> top-k -> top-p -> softmax -> argmax(p / Exp(1) noise)      (one CTA of 1024 threads per row)
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int SMP_THREADS = 1024;
+
+__device__ __forceinline__ uint32_t float_order(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+struct SampleArgs {
+    const float *logits;        // (B, V)
+    int64_t *tokens;            // (B, max_len, 2)
+    float *hist;                // masked logits out: row b at hist + b*hist_row_stride (+ j*V when st given) or NULL
+    const float *noise_sample;  // (B, V)
+    const float *noise_best;    // (B, V)
+    int V, npad, max_len;
+    int L, L_cond, tuple_i;     // used when st == NULL
+    int64_t end0, end1;
+    int top_k;
+    float top_p, temperature;
+    int best_in_first, mask_invalid, mask_invalid_completion;
+    const int32_t *st;          // device state or NULL
+    int64_t hist_row_stride;    // floats between rows of the history (= max_steps * V)
+    int64_t noise_step_stride;  // floats between steps in the noise slab (= 4 * B * Vmax)
+    int noise_row_stride;       // floats between rows of one noise draw (= Vmax)
+};
+
+__global__ void __launch_bounds__(SMP_THREADS) ar_sample_kernel(SampleArgs a) {
+    extern __shared__ __align__(16) unsigned char smp_smem[];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smp_smem);   // [npad]
+    float *ev = reinterpret_cast<float *>(smp_smem + (size_t)a.npad * 8);           // [npad] exp(l_i - l_0), sorted order
+    __shared__ double warp_tot[32];
+    __shared__ float red_f[32];
+    __shared__ int red_i[32];
+    __shared__ int sh_nkeep, sh_n2;
+    __shared__ float sh_sum;
+
+    const int b = blockIdx.x, tid = threadIdx.x, V = a.V, npad = a.npad;
+    const int L = a.st ? a.st[ST_LEN] : a.L;
+    const int L_cond = a.st ? a.st[ST_LCOND] : a.L_cond;
+    const int step_j = L - L_cond;
+    const int64_t *row = a.tokens + (size_t)b * a.max_len * 2;
+    const float *lg = a.logits + (size_t)b * V;
+    const bool greedy = a.best_in_first && b == 0;
+    const int top_k = greedy ? 1 : a.top_k;
+    const float top_p = greedy ? 0.001f : a.top_p;
+    size_t noise_off = (size_t)b * a.noise_row_stride;
+    if (a.st) noise_off += (size_t)a.st[ST_CHUNK] * a.noise_step_stride;
+    const float *q = (greedy ? a.noise_best : a.noise_sample) + noise_off;
+    float *hist = a.hist ? a.hist + (size_t)b * a.hist_row_stride + (a.st ? (size_t)a.st[ST_STEPS] * V : 0) : nullptr;
+
+    // ---- masker (representers.py:120-155)
+    const int64_t last = row[2 * (L - 1)];
+    int64_t nxt = 0;
+    bool val_forced = false;
+    if (a.tuple_i == 1) {
+        val_forced = row[2 * L] == a.end0;
+    } else if (a.mask_invalid_completion) {
+        // cond_poses = cat(cond_pos, [end0 + 1]); searchsorted(right=True) -> first entry > last
+        int lo = 0, hi = L_cond;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (row[2 * mid] > last) hi = mid; else lo = mid + 1;
+        }
+        nxt = lo < L_cond ? row[2 * lo] : a.end0 + 1;
+    }
+    for (int v = tid; v < npad; v += SMP_THREADS) {
+        unsigned long long key = 0ull;
+        if (v < V) {
+            float x = lg[v];
+            if (a.tuple_i == 1) {
+                if (val_forced) x = (v == a.end1) ? 1.0f : -INFINITY;
+            } else {
+                if (a.mask_invalid && step_j > 0 && v <= last && v != a.end0) x = -INFINITY;
+                if (a.mask_invalid_completion && v > nxt) x = -INFINITY;
+            }
+            if (hist) hist[v] = x;
+            const float l = x / a.temperature;
+            key = ((unsigned long long)float_order(l) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)v);
+        }
+        keys[v] = key;
+    }
+    __syncthreads();
+
+    // ---- bitonic sort, descending by (value, then lower index first)
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < (npad >> 1); i += SMP_THREADS) {
+                const int lo = i & (j - 1);
+                const int ia = ((i - lo) << 1) + lo, ib = ia + j;
+                const bool desc = (ia & k) == 0;
+                const unsigned long long ka = keys[ia], kb = keys[ib];
+                if ((ka < kb) == desc) { keys[ia] = kb; keys[ib] = ka; }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- top-k: keep everything >= the k-th largest (ties kept) — common.py:265-269
+    if (tid == 0) sh_nkeep = V;
+    __syncthreads();
+    const int kk = min(top_k, V);
+    if (kk > 0) {
+        const uint32_t kth = (uint32_t)(keys[kk - 1] >> 32);
+        for (int i = tid; i < V; i += SMP_THREADS) {
+            const uint32_t oi = (uint32_t)(keys[i] >> 32);
+            const uint32_t on = (i + 1 < V) ? (uint32_t)(keys[i + 1] >> 32) : 0u;
+            if (oi >= kth && (i + 1 == V || on < kth)) sh_nkeep = i + 1;
+        }
+    }
+    __syncthreads();
+    const int nkeep = sh_nkeep;
+
+    // ---- e_i = exp(l_i - l_0) for the kept prefix (softmax numerators in sorted order)
+    auto sorted_val = [&](int i) -> float {
+        const uint32_t o = (uint32_t)(keys[i] >> 32);
+        const uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+        return __uint_as_float(u);
+    };
+    const float l0 = sorted_val(0);
+    float part = 0.f;
+    for (int i = tid; i < npad; i += SMP_THREADS) {
+        float e = 0.f;
+        if (i < nkeep) e = expf(sorted_val(i) - l0);  // -inf -> 0
+        ev[i] = e;
+        part += e;
+    }
+    part = warp_sum(part);
+    if ((tid & 31) == 0) red_f[tid >> 5] = part;
+    __syncthreads();
+    if (tid < 32) {
+        float t = red_f[tid];
+        t = warp_sum(t);
+        if (tid == 0) sh_sum = t;
+    }
+    __syncthreads();
+
+    // ---- top-p: keep i == 0 or cumsum(p)[i-1] <= top_p (common.py:271-284); cumsum accumulated in fp64 like ATen's
+    //      CPU cumsum (acc_type<float> = double) and rounded to fp32 before the comparison
+    int n2 = nkeep;
+    if (top_p > 0.0f) {
+        const float sum1 = sh_sum;
+        const int per = npad / SMP_THREADS > 0 ? npad / SMP_THREADS : 1;
+        const int i0 = tid * per;
+        double loc = 0.0;
+        for (int u = 0; u < per; ++u) {
+            const int i = i0 + u;
+            if (i < npad) loc += (double)(ev[i] / sum1);
+        }
+        // block exclusive scan of `loc`
+        double inc = loc;
+        const int lane = tid & 31, w = tid >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += up;
+        }
+        if (lane == 31) warp_tot[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            double t = warp_tot[lane];
+            double ti = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double up = __shfl_up_sync(0xffffffffu, ti, o);
+                if (lane >= o) ti += up;
+            }
+            warp_tot[lane] = ti - t;  // exclusive
+        }
+        __syncthreads();
+        double run = warp_tot[w] + (inc - loc);
+        int cnt = 0;
+        for (int u = 0; u < per; ++u) {
+            const int i = i0 + u;
+            if (i < nkeep) {
+                run += (double)(ev[i] / sum1);
+                if (!((float)run > top_p)) ++cnt;
+            }
+        }
+        // block sum of cnt
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) red_i[w] = cnt;
+        __syncthreads();
+        if (tid < 32) {
+            int t = red_i[tid];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (tid == 0) sh_n2 = min(nkeep, 1 + t);
+        }
+        __syncthreads();
+        n2 = sh_n2;
+    }
+
+    // ---- softmax over the survivors and the multinomial draw as argmax(p_i / q_i) (common.py:293-297)
+    float s2 = 0.f;
+    for (int i = tid; i < n2; i += SMP_THREADS) s2 += ev[i];
+    s2 = warp_sum(s2);
+    __syncthreads();
+    if ((tid & 31) == 0) red_f[tid >> 5] = s2;
+    __syncthreads();
+    if (tid < 32) {
+        float t = warp_sum(red_f[tid]);
+        if (tid == 0) sh_sum = t;
+    }
+    __syncthreads();
+    const float sum2 = sh_sum;
+    float best = -1.0f;
+    int best_v = 0x7fffffff;
+    for (int i = tid; i < n2; i += SMP_THREADS) {
+        const int v = (int)(0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull));
+        const float sc = (ev[i] / sum2) / q[v];
+        if (sc > best || (sc == best && v < best_v)) { best = sc; best_v = v; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+        if (ob > best || (ob == best && ov < best_v)) { best = ob; best_v = ov; }
+    }
+    if ((tid & 31) == 0) { red_f[tid >> 5] = best; red_i[tid >> 5] = best_v; }
+    __syncthreads();
+    if (tid < 32) {
+        best = red_f[tid]; best_v = red_i[tid];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+            if (ob > best || (ob == best && ov < best_v)) { best = ob; best_v = ov; }
+        }
+        if (tid == 0) a.tokens[((size_t)b * a.max_len + L) * 2 + a.tuple_i] = (int64_t)best_v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------------------------------
+int launch_state_init(int32_t *st, int L_cond, cudaStream_t s) {
+    ar_state_init_kernel<<<1, 32, 0, s>>>(st, L_cond);
+    return check_launch("ar_state_init");
+}
+int launch_chunk_reset(int32_t *st, cudaStream_t s) {
+    ar_chunk_reset_kernel<<<1, 32, 0, s>>>(st);
+    return check_launch("ar_chunk_reset");
+}
+int launch_advance(int32_t *st, const int64_t *tokens, int B, int max_len, int64_t end0, int64_t end1, cudaStream_t s) {
+    ar_advance_kernel<<<1, 128, 0, s>>>(st, tokens, B, max_len, end0, end1);
+    return check_launch("ar_advance");
+}
+int launch_embed(const int64_t *tokens, const float *emb0, const float *emb1, const float *embx, const float *pos_emb,
+                 const float *cond_pos_emb, float *x, int B, int d, int max_len, int t0, int T, int L_cond, int64_t end0,
+                 const int32_t *st, cudaStream_t s) {
+    if (T <= 0) return SFB200_OK;
+    ar_embed_kernel<<<dim3(T, B), 256, 0, s>>>(tokens, emb0, emb1, embx, pos_emb, cond_pos_emb, x, d, max_len, t0, T, L_cond,
+                                               end0, st);
+    return check_launch("ar_embed");
+}
+int launch_add_target(const float *x_in, float *x_out, const int64_t *tokens, const float *emb0, int B, int d, int max_len,
+                      int t0, int T, const int32_t *st, cudaStream_t s, int Tin) {
+    if (T <= 0) return SFB200_OK;
+    ar_add_target_kernel<<<dim3(T, B), 256, 0, s>>>(x_in, x_out, tokens, emb0, d, max_len, t0, T, Tin, st);
+    return check_launch("ar_add_target");
+}
+int launch_take_last(const float *x, float *out, int B, int d, int T, cudaStream_t s) {
+    ar_take_last_kernel<<<B, 256, 0, s>>>(x, out, d, T);
+    return check_launch("ar_take_last");
+}
+int launch_layernorm(const float *x, const float *w, const float *b, float *y, int rows, int d, cudaStream_t s) {
+    if (rows <= 0) return SFB200_OK;
+    if (d % 4 != 0) return SFB200_E_ARG;
+    layernorm_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, w, b, y, rows, d);
+    return check_launch("layernorm");
+}
+int launch_attn_decode(const float *qkv, float *kc, float *vc, float *out, float *part, int B, int H, int max_len, int pos,
+                       const int32_t *st, int n_split, cudaStream_t s) {
+    if (n_split < 1 || (n_split > 1 && !part)) return SFB200_E_ARG;
+    attn_decode_kernel<<<dim3(H, B, n_split), 128, 0, s>>>(qkv, kc, vc, out, part, H, max_len, pos, st, n_split);
+    SFB_TRY(check_launch("attn_decode"));
+    if (n_split > 1) {
+        attn_combine_kernel<<<dim3(H, B), 64, 0, s>>>(part, out, H, n_split);
+        SFB_TRY(check_launch("attn_combine"));
+    }
+    return SFB200_OK;
+}
+int launch_attn_prefill(const float *qkv, float *kc, float *vc, float *out, int B, int H, int T, int max_len,
+                        cudaStream_t s) {
+    if (T <= 0) return SFB200_OK;
+    attn_prefill_kernel<<<dim3(H, B, (T + 7) / 8), 256, 0, s>>>(qkv, kc, vc, out, H, T, max_len);
+    return check_launch("attn_prefill");
+}
+
+int launch_sample(const SampleLaunch &p, cudaStream_t s) {
+    if (p.V < 1 || p.V > 8192) return SFB200_E_ARG;
+    int npad = 1024;  // >= SMP_THREADS so that every thread owns >= 1 scan slot
+    while (npad < p.V) npad <<= 1;
+    SampleArgs a;
+    a.logits = p.logits; a.tokens = p.tokens; a.hist = p.hist; a.noise_sample = p.noise_sample; a.noise_best = p.noise_best;
+    a.V = p.V; a.npad = npad; a.max_len = p.max_len; a.L = p.L; a.L_cond = p.L_cond; a.tuple_i = p.tuple_i;
+    a.end0 = p.end0; a.end1 = p.end1; a.top_k = p.sp.top_k; a.top_p = p.sp.top_p; a.temperature = p.sp.temperature;
+    a.best_in_first = p.sp.best_in_first; a.mask_invalid = p.sp.mask_invalid;
+    a.mask_invalid_completion = p.sp.mask_invalid_completion;
+    a.st = p.st; a.hist_row_stride = p.hist_row_stride; a.noise_step_stride = p.noise_step_stride;
+    a.noise_row_stride = p.noise_row_stride > 0 ? p.noise_row_stride : p.V;
+    const size_t smem = (size_t)npad * 12;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SFB_CUDA_TRY(cudaFuncSetAttribute(ar_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12));
+        attr_done = true;
+    }
+    ar_sample_kernel<<<p.B, SMP_THREADS, smem, s>>>(a);
+    return check_launch("ar_sample");
+}
+
+}  // namespace sfb

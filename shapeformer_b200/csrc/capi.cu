@@ -1,0 +1,93 @@
+// extern "C" surface of libsfb200 (declared in include/sfb200.h); thin argument checks + dispatch to the launchers.
+#include <stdio.h>
+#include <string.h>
+
+#include "ar_kernels.cuh"
+#include "decoder_kernels.cuh"
+
+namespace sfb {
+static thread_local char g_err[512] = "";
+void set_cuda_error(cudaError_t e, const char *where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+}  // namespace sfb
+
+using namespace sfb;
+
+extern "C" {
+
+int sfb200_version(void) { return SFB200_VERSION; }
+
+const char *sfb200_error_string(int code) {
+    switch (code) {
+        case SFB200_OK: return "ok";
+        case SFB200_E_ARG: return "invalid argument or unsupported shape";
+        case SFB200_E_CUDA: return "CUDA error (see sfb200_last_cuda_error)";
+        case SFB200_E_STATE: return "call order violated";
+    }
+    return "unknown error";
+}
+const char *sfb200_last_cuda_error(void) { return g_err; }
+
+int sfb200_code_gather(const int64_t *code_ind, const float *codebook, float *out, int B, int cells, int C, int n_codes,
+                       void *stream) {
+    if (!code_ind || !codebook || !out) return SFB200_E_ARG;
+    return launch_code_gather(code_ind, codebook, out, B, cells, C, n_codes, as_stream(stream));
+}
+int sfb200_grid_to_channels_last(const float *src, float *dst, int B, int C, int64_t S, void *stream) {
+    if (!src || !dst) return SFB200_E_ARG;
+    return launch_to_channels_last(src, dst, B, C, S, as_stream(stream));
+}
+int sfb200_decoder_set_weights(const float *mlp_weights, void *stream) {
+    if (!mlp_weights) return SFB200_E_ARG;
+    SFB_TRY(decoder_set_weights_ffma(mlp_weights, as_stream(stream)));
+    return decoder_set_weights_tc(mlp_weights, as_stream(stream));
+}
+int sfb200_decoder_points(const float *grid, const float *xtg, int64_t xtg_batch_stride, float *logits, int B, int R,
+                          int64_t N, int impl, void *stream) {
+    if (!grid || !xtg || !logits) return SFB200_E_ARG;
+    if (impl == 1) return launch_decoder_points_ffma(grid, xtg, xtg_batch_stride, logits, B, R, N, as_stream(stream));
+    if (impl == 0) return launch_decoder_points_tc(grid, xtg, xtg_batch_stride, logits, B, R, N, as_stream(stream));
+    return SFB200_E_ARG;
+}
+int sfb200_tokens_to_dense(const int64_t *tokens, const int64_t *empty_index, int64_t *dense, int B, int T, int cells,
+                           int64_t end_pos, int64_t end_val, void *stream) {
+    if (!tokens || !empty_index || !dense) return SFB200_E_ARG;
+    return launch_tokens_to_dense(tokens, empty_index, dense, B, T, cells, end_pos, end_val, as_stream(stream));
+}
+
+int sfb200_linear(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
+                  int act, void *stream) {
+    if (!x || !W || !y || (act != 0 && act != 1)) return SFB200_E_ARG;
+    return launch_linear(x, W, bias, residual, y, M, N, K, act, as_stream(stream));
+}
+int sfb200_layernorm(const float *x, const float *w, const float *b, float *y, int rows, int d, void *stream) {
+    if (!x || !w || !b || !y) return SFB200_E_ARG;
+    return launch_layernorm(x, w, b, y, rows, d, as_stream(stream));
+}
+int sfb200_attn_decode(const float *qkv, float *kcache, float *vcache, float *out, float *part, int B, int H, int max_len,
+                       int pos, const int32_t *pos_dev, int n_split, void *stream) {
+    if (!qkv || !kcache || !vcache || !out || B < 1 || H < 1 || pos < 0 || pos >= max_len) return SFB200_E_ARG;
+    if (pos_dev) return SFB200_E_ARG;  // device-side position is an engine-internal mode (state words)
+    return launch_attn_decode(qkv, kcache, vcache, out, part, B, H, max_len, pos, nullptr, n_split, as_stream(stream));
+}
+int sfb200_attn_prefill(const float *qkv, float *kcache, float *vcache, float *out, int B, int H, int T, int max_len,
+                        void *stream) {
+    if (!qkv || !kcache || !vcache || !out || B < 1 || H < 1 || T < 0 || T > max_len) return SFB200_E_ARG;
+    return launch_attn_prefill(qkv, kcache, vcache, out, B, H, T, max_len, as_stream(stream));
+}
+int sfb200_ar_sample(const float *logits, int64_t *tokens, float *hist_out, const float *noise_sample,
+                     const float *noise_best, int B, int V, int max_len, int L, int L_cond, int tuple_i,
+                     const int64_t *end_tokens, const sfb200_ar_sampling *sp, void *stream) {
+    if (!logits || !tokens || !noise_sample || !noise_best || !end_tokens || !sp) return SFB200_E_ARG;
+    if (B < 1 || L < 1 || L >= max_len || L_cond < 1 || L_cond > L || (tuple_i != 0 && tuple_i != 1)) return SFB200_E_ARG;
+    if (!(sp->temperature > 0.f)) return SFB200_E_ARG;
+    SampleLaunch p;
+    p.logits = logits; p.tokens = tokens; p.hist = hist_out; p.noise_sample = noise_sample; p.noise_best = noise_best;
+    p.B = B; p.V = V; p.max_len = max_len; p.L = L; p.L_cond = L_cond; p.tuple_i = tuple_i;
+    p.end0 = end_tokens[0]; p.end1 = end_tokens[1]; p.sp = *sp; p.st = nullptr;
+    p.hist_row_stride = V; p.noise_step_stride = 0; p.noise_row_stride = V;
+    return launch_sample(p, as_stream(stream));
+}
+
+}  // extern "C"

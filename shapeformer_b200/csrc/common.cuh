@@ -1,0 +1,68 @@
+// Shared device/host helpers for libsfb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/sfb200.h"
+
+namespace sfb {
+
+void set_cuda_error(cudaError_t e, const char *where);
+
+// Returns SFB200_OK or SFB200_E_CUDA after recording the message.
+static inline int check_launch(const char *where) {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_cuda_error(e, where);
+        return SFB200_E_CUDA;
+    }
+    return SFB200_OK;
+}
+
+#define SFB_CUDA_TRY(expr)                                   \
+    do {                                                     \
+        cudaError_t _e = (expr);                             \
+        if (_e != cudaSuccess) {                             \
+            ::sfb::set_cuda_error(_e, #expr);                \
+            return SFB200_E_CUDA;                            \
+        }                                                    \
+    } while (0)
+
+#define SFB_TRY(expr)                 \
+    do {                              \
+        int _r = (expr);              \
+        if (_r != SFB200_OK) return _r; \
+    } while (0)
+
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+
+// streaming (evict-first) 128-bit load for data touched once per launch (KV cache, weights)
+__device__ __forceinline__ float4 ld4_stream(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, int src_bytes) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace sfb

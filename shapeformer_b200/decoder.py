@@ -1,0 +1,145 @@
+"""Host side of the VQDIF decoder path: VQDIF.decode_index (reference shapeformer/models/vqdif/vqdif.py:60-76) =
+codebook gather -> UNet3D + Upsampler conv prologue -> fused per-point kernel (trilinear feature sampling + ResNet-FC MLP).
+
+The gather, the layout change and the per-point kernel are libsfb200 kernels.  The conv prologue (SURVEY.md §8a row D1:
+"cuDNN first, custom later") runs the reference's own op set through PyTorch/cuDNN in strict fp32 (TF32 off).
+"""
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+
+def pack_mlp_weights(sd, prefix="decoder."):
+    """fc_p, then per block (fc_c, fc_0, fc_1) as [weight (out,in) row-major, bias], then fc_out — the order
+    decoder_kernels.cu expects (SFB200_DEC_MLP_FLOATS floats)."""
+    parts = [sd[prefix + "fc_p.weight"], sd[prefix + "fc_p.bias"]]
+    for i in range(5):
+        for nm in (f"fc_c.{i}", f"blocks.{i}.fc_0", f"blocks.{i}.fc_1"):
+            parts += [sd[prefix + nm + ".weight"], sd[prefix + nm + ".bias"]]
+    parts += [sd[prefix + "fc_out.weight"], sd[prefix + "fc_out.bias"]]
+    flat = torch.cat([p.detach().reshape(-1).float() for p in parts])
+    if flat.numel() != _lib.DEC_MLP_FLOATS:
+        raise _lib.Sfb200Error(f"LocalDecoder MLP must be hidden=c_dim=32, n_blocks=5 (got {flat.numel()} floats)")
+    return flat
+
+
+def _gcr(sd, pre, x):
+    """'gcr' SingleConv (vqdif/unet3d.py:18-92)."""
+    x = F.group_norm(x, 8, sd[pre + "groupnorm.weight"], sd[pre + "groupnorm.bias"], 1e-5)
+    return F.relu_(F.conv3d(x, sd[pre + "conv.weight"], None, padding=1))
+
+
+def _crg(sd, pre, x):
+    """'crg' ConvLayer (vqdif/updown.py:79-99)."""
+    x = F.relu_(F.conv3d(x, sd[pre + "conv.weight"], None, padding=1))
+    return F.group_norm(x, 8, sd[pre + "groupnorm.weight"], sd[pre + "groupnorm.bias"], 1e-5)
+
+
+def conv_prologue(sd, x, prefix="decoder."):
+    """UNet3D (3 levels, DoubleConv 'gcr', max-pool 2, nearest up + concat, 1x1 final conv — vqdif/unet3d.py:449-474)
+    followed by the Upsampler (2 x [nearest x2, 'crg', 'crg'] — vqdif/updown.py:119-132), strict fp32."""
+    u = prefix + "unet3d."
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        feats = []
+        for i in range(3):
+            if i > 0:
+                x = F.max_pool3d(x, 2)
+            x = _gcr(sd, f"{u}encoders.{i}.basic_module.SingleConv1.", x)
+            x = _gcr(sd, f"{u}encoders.{i}.basic_module.SingleConv2.", x)
+            feats.insert(0, x)
+        for i, skip in enumerate(feats[1:]):
+            x = F.interpolate(x, size=skip.shape[2:], mode="nearest")
+            x = torch.cat([skip, x], 1)
+            x = _gcr(sd, f"{u}decoders.{i}.basic_module.SingleConv1.", x)
+            x = _gcr(sd, f"{u}decoders.{i}.basic_module.SingleConv2.", x)
+        x = F.conv3d(x, sd[u + "final_conv.weight"], sd[u + "final_conv.bias"])
+        up = prefix + "upsampler."
+        for s in range(2):
+            x = F.interpolate(x, scale_factor=2, mode="nearest")
+            x = _crg(sd, f"{up}blocks.{3 * s + 1}.", x)
+            x = _crg(sd, f"{up}blocks.{3 * s + 2}.", x)
+    return x
+
+
+class ImplicitDecoder:
+    """decode_index for batches of code grids.  `sd`: VQDIF state dict (decoder.*, quantizer.embedding.weight) on the
+    target CUDA device."""
+    _active = None   # which instance's MLP weights currently sit in the library's constant bank
+
+    def __init__(self, sd, device, impl=0, prefix="decoder.", codebook_key="quantizer.embedding.weight"):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.Sfb200Error("ImplicitDecoder needs a CUDA device (no CPU fallback)")
+        self.prefix, self.impl = prefix, impl
+        self.sd = {k: v.detach().to(self.device, torch.float32).contiguous() for k, v in sd.items()
+                   if k.startswith(prefix) or k == codebook_key}
+        self.codebook = self.sd[codebook_key]
+        self.mlp = pack_mlp_weights(self.sd, prefix).to(self.device).contiguous()
+
+    def _activate(self):
+        if ImplicitDecoder._active is not self:
+            _lib.check(self.lib.sfb200_decoder_set_weights(_lib.ptr(self.mlp), _lib.stream_ptr()), "decoder_set_weights")
+            ImplicitDecoder._active = self
+
+    def get_code(self, code_ind):
+        """Quantizer.get_code: (B,R,R,R) int64 -> (B,C,R,R,R) fp32."""
+        B = code_ind.shape[0]
+        R = code_ind.shape[1:]
+        cells = int(torch.tensor(R).prod())
+        ind = code_ind.to(self.device).long().contiguous()
+        n_codes, C = self.codebook.shape
+        out = torch.empty(B, C, *R, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.sfb200_code_gather(_lib.ptr(ind), _lib.ptr(self.codebook), _lib.ptr(out), B, cells, C, n_codes,
+                                               _lib.stream_ptr()), "code_gather")
+        return out
+
+    def feature_grid(self, quant_feat):
+        """(B,128,16,16,16) quantised features -> channel-last (B,64,64,64,32) decoder feature grid."""
+        g = conv_prologue(self.sd, quant_feat, self.prefix).contiguous()
+        B, C = g.shape[:2]
+        S = g.shape[2] * g.shape[3] * g.shape[4]
+        out = torch.empty(B, g.shape[2], g.shape[3], g.shape[4], C, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.sfb200_grid_to_channels_last(_lib.ptr(g), _lib.ptr(out), B, C, S, _lib.stream_ptr()),
+                   "grid_to_channels_last")
+        return out
+
+    def decode_points(self, grid_cl, Xtg, impl=None):
+        """grid_cl (B,R,R,R,32), Xtg (B or 1, N, 3) in [-1,1] -> logits (B, N)."""
+        B, R = grid_cl.shape[0], grid_cl.shape[1]
+        if grid_cl.shape[-1] != 32 or grid_cl.shape[2] != R or grid_cl.shape[3] != R:
+            raise _lib.Sfb200Error("feature grid must be (B,R,R,R,32)")
+        # float64 queries (reference decode_sample_indices, shapeformer.py:383) are rounded to fp32 first: <= 1 ulp of the
+        # coordinate away from the reference's normalise-in-fp64-then-.float()
+        x = Xtg.to(self.device, torch.float32).contiguous()
+        if x.dim() != 3 or x.shape[-1] != 3 or x.shape[0] not in (1, B):
+            raise _lib.Sfb200Error("Xtg must be (B or 1, N, 3)")
+        N = x.shape[1]
+        stride = 0 if (x.shape[0] == 1 and B > 1) else N * 3
+        out = torch.empty(B, N, dtype=torch.float32, device=self.device)
+        self._activate()
+        _lib.check(self.lib.sfb200_decoder_points(_lib.ptr(grid_cl), _lib.ptr(x), stride, _lib.ptr(out), B, R, N,
+                                                  self.impl if impl is None else impl, _lib.stream_ptr()),
+                   "decoder_points")
+        return out
+
+    def decode(self, quant_feat, Xtg, impl=None):
+        """VQDIF.decode (vqdif/vqdif.py:60-72); the 256^3 chunking is unnecessary (N is an int64 in the kernel)."""
+        return {"logits": self.decode_points(self.feature_grid(quant_feat), Xtg, impl)[..., None]}
+
+    def decode_index(self, code_ind, Xtg, impl=None):
+        """VQDIF.decode_index (vqdif/vqdif.py:74-76)."""
+        return self.decode(self.get_code(code_ind), Xtg, impl)
+
+    def tokens_to_dense(self, tokens, empty_index, res=16, end_tokens=(4096, 4096)):
+        """filter_end_tokens + batch_sparse2dense for every row (shapeformer/common.py:50-55,171-189):
+        tokens (B,T,2) int64, empty_index (B,) int64 -> (B,res,res,res) int64."""
+        B, T, _ = tokens.shape
+        tok = tokens.to(self.device).long().contiguous()
+        emp = empty_index.to(self.device).long().reshape(B).contiguous()
+        dense = torch.empty(B, res, res, res, dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.sfb200_tokens_to_dense(_lib.ptr(tok), _lib.ptr(emp), _lib.ptr(dense), B, T, res ** 3,
+                                                   int(end_tokens[0]), int(end_tokens[1]), _lib.stream_ptr()),
+                   "tokens_to_dense")
+        return dense

@@ -1,0 +1,68 @@
+"""Thin Python wrappers over the individual libsfb200 operators (the same kernels the AR engine enqueues); used by the
+parity tests and for profiling single kernels.  Device tensors in, device tensors out, current CUDA stream."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def linear(x, W, bias=None, residual=None, act=None):
+    """y = act(x @ W.T + bias) + residual  (nn.Linear; act in {None, "gelu"})."""
+    lib = _lib.load()
+    M, K = x.shape
+    N = W.shape[0]
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    _lib.check(lib.sfb200_linear(_lib.ptr(x), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(residual), _lib.ptr(y), M, N, K,
+                                 1 if act == "gelu" else 0, _lib.stream_ptr()), "sfb200_linear")
+    return y
+
+
+def layernorm(x, w, b):
+    lib = _lib.load()
+    rows, d = x.shape
+    y = torch.empty_like(x)
+    _lib.check(lib.sfb200_layernorm(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), rows, d, _lib.stream_ptr()),
+               "sfb200_layernorm")
+    return y
+
+
+def attn_decode(qkv, kcache, vcache, pos, n_split=1):
+    """qkv (B,3d); caches (B,H,max_len,64) updated in place at `pos`; returns (B,d)."""
+    lib = _lib.load()
+    B = qkv.shape[0]
+    _, H, max_len, hd = kcache.shape
+    assert hd == 64
+    out = torch.empty(B, H * 64, dtype=torch.float32, device=qkv.device)
+    part = torch.empty(B * H * n_split * 66, dtype=torch.float32, device=qkv.device) if n_split > 1 else None
+    _lib.check(lib.sfb200_attn_decode(_lib.ptr(qkv), _lib.ptr(kcache), _lib.ptr(vcache), _lib.ptr(out), _lib.ptr(part), B, H,
+                                      max_len, pos, None, n_split, _lib.stream_ptr()), "sfb200_attn_decode")
+    return out
+
+
+def attn_prefill(qkv, kcache, vcache):
+    """qkv (B,T,3d); fills caches [0,T); returns (B,T,d)."""
+    lib = _lib.load()
+    B, T, _ = qkv.shape
+    _, H, max_len, _ = kcache.shape
+    out = torch.empty(B, T, H * 64, dtype=torch.float32, device=qkv.device)
+    _lib.check(lib.sfb200_attn_prefill(_lib.ptr(qkv), _lib.ptr(kcache), _lib.ptr(vcache), _lib.ptr(out), B, H, T, max_len,
+                                       _lib.stream_ptr()), "sfb200_attn_prefill")
+    return out
+
+
+def ar_sample(logits, tokens, L, L_cond, tuple_i, noise_sample, noise_best, end_tokens=(4096, 4096), top_k=100, top_p=0.8,
+              temperature=1.0, best_in_first=False, mask_invalid=True, mask_invalid_completion=False, want_hist=True):
+    """One masked + filtered categorical draw per row; writes tokens[:, L, tuple_i] in place.  Returns masked logits."""
+    lib = _lib.load()
+    B, V = logits.shape
+    max_len = tokens.shape[1]
+    hist = torch.empty(B, V, dtype=torch.float32, device=logits.device) if want_hist else None
+    et = (ctypes.c_int64 * 2)(int(end_tokens[0]), int(end_tokens[1]))
+    sp = _lib.ArSampling(int(top_k), float(top_p), float(temperature), int(bool(best_in_first)), int(bool(mask_invalid)),
+                         int(bool(mask_invalid_completion)))
+    _lib.check(lib.sfb200_ar_sample(_lib.ptr(logits), _lib.ptr(tokens), _lib.ptr(hist), _lib.ptr(noise_sample),
+                                    _lib.ptr(noise_best), B, V, max_len, L, L_cond, tuple_i,
+                                    ctypes.cast(et, ctypes.c_void_p), ctypes.byref(sp), _lib.stream_ptr()),
+               "sfb200_ar_sample")
+    return hist
