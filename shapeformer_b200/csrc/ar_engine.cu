@@ -127,6 +127,7 @@ struct sfb200_ar {
     sfb200_ar_sampling sp;
     // graph
     cudaGraphExec_t gexec;
+    cudaStream_t cap_stream;   // private stream used only to record the step graph (the legacy default stream cannot capture)
     const float *g_noise;
     int g_B;
     sfb200_ar_sampling g_sp;
@@ -204,6 +205,7 @@ int sfb200_ar_create(const sfb200_ar_config *cfg, const float *weights, void *kv
 void sfb200_ar_destroy(sfb200_ar *h) {
     if (!h) return;
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     free(h);
 }
 
@@ -337,9 +339,10 @@ extern "C" int sfb200_ar_steps(sfb200_ar *h, int n_steps, const float *noise, in
                 done = 1;
             }
             cudaGraph_t graph = nullptr;
-            SFB_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            const int r = enqueue_step(h, noise, s);
-            const cudaError_t e = cudaStreamEndCapture(s, &graph);
+            if (!h->cap_stream) SFB_CUDA_TRY(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+            SFB_CUDA_TRY(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+            const int r = enqueue_step(h, noise, h->cap_stream);
+            const cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
             if (r != SFB200_OK) { if (graph) cudaGraphDestroy(graph); return r; }
             SFB_CUDA_TRY(e);
             const cudaError_t ei = cudaGraphInstantiate(&h->gexec, graph, 0);

@@ -408,11 +408,12 @@ __device__ __forceinline__ void attn_stream_keys(SoftState &st, const float4 q4,
 }
 
 // Merge the per-half-warp states of one CTA (NG groups).  Result (unnormalised acc, M, Lsum) valid in warp 0, where
-// lane handles dims 2*lane, 2*lane+1.
+// lane handles dims 2*lane, 2*lane+1.  Group stride is 68 floats so that the float4 stores stay 16-byte aligned.
+constexpr int MRG = 68;
 template <int NG>
-__device__ __forceinline__ void attn_merge(const SoftState &st, int grp, int c, float *sm /* NG*66 */, float &M,
+__device__ __forceinline__ void attn_merge(const SoftState &st, int grp, int c, float *sm /* NG*MRG */, float &M,
                                            float &Ls, float &o0, float &o1) {
-    float *mine = sm + grp * 66;
+    float *mine = sm + grp * MRG;
     if (c == 0) { mine[64] = st.m; mine[65] = st.l; }
     st4(mine + c * 4, st.acc);
     __syncthreads();
@@ -420,15 +421,15 @@ __device__ __forceinline__ void attn_merge(const SoftState &st, int grp, int c, 
         const int lane = threadIdx.x;
         M = -INFINITY;
 #pragma unroll
-        for (int g = 0; g < NG; ++g) M = fmaxf(M, sm[g * 66 + 64]);
+        for (int g = 0; g < NG; ++g) M = fmaxf(M, sm[g * MRG + 64]);
         Ls = 0.f; o0 = 0.f; o1 = 0.f;
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
-            const float mg = sm[g * 66 + 64];
+            const float mg = sm[g * MRG + 64];
             const float w = (mg == -INFINITY) ? 0.f : expf(mg - M);
-            Ls = fmaf(sm[g * 66 + 65], w, Ls);
-            o0 = fmaf(sm[g * 66 + 2 * lane], w, o0);
-            o1 = fmaf(sm[g * 66 + 2 * lane + 1], w, o1);
+            Ls = fmaf(sm[g * MRG + 65], w, Ls);
+            o0 = fmaf(sm[g * MRG + 2 * lane], w, o0);
+            o1 = fmaf(sm[g * MRG + 2 * lane + 1], w, o1);
         }
     }
 }
@@ -437,7 +438,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const float *__restric
                                                           float *__restrict__ out, float *__restrict__ part, int H,
                                                           int max_len, int pos_arg, const int32_t *__restrict__ st_dev,
                                                           int n_split) {
-    __shared__ float sm[8 * 66];
+    __shared__ __align__(16) float sm[8 * MRG];
     const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z;
     const int pos = st_dev ? st_dev[ST_LEN] - 1 : pos_arg;
     const int d = H * 64;

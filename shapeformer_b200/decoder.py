@@ -67,7 +67,7 @@ class ImplicitDecoder:
     target CUDA device."""
     _active = None   # which instance's MLP weights currently sit in the library's constant bank
 
-    def __init__(self, sd, device, impl=0, prefix="decoder.", codebook_key="quantizer.embedding.weight"):
+    def __init__(self, sd, device, impl=1, prefix="decoder.", codebook_key="quantizer.embedding.weight"):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":

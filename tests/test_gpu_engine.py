@@ -1,0 +1,145 @@
+"""GPU parity of the whole hot path against the oracle and the committed reference fixtures."""
+import pytest
+import torch
+
+from oracle import sf_oracle as O
+from shapeformer_b200 import ar, decoder, synth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+END = (4096, 4096)
+
+
+def make_sampler(cuda, cfg, sd, B, Lc, steps, **kw):
+    blob = ar.pack_gpt_weights(sd, cfg, cuda)
+    return ar.ARSampler(blob, cfg, END, max_rows=B, max_cond=Lc, max_steps=steps, keep_history=True, **kw)
+
+
+@pytest.mark.parametrize("path", util.sampler_goldens())
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_sampler_reproduces_reference_golden(cuda, path, use_graph):
+    """Token sequences bit-exact vs the REFERENCE's sample_indices (fixture), logits history within 5e-5."""
+    g = torch.load(path)
+    cfg = synth.TINY_GPT
+    wseed, cseed, rseed = g["seeds"]
+    sd = synth.gpt_state_dict(cfg, seed=wseed, peaky=True)
+    c = synth.cond_indices(g["B"], g["L_c"], seed=cseed, shared=True)
+    noise = util.noise_from_seed(rseed, g["steps"], g["B"], 4097)
+    s = make_sampler(cuda, cfg, sd, g["B"], g["L_c"], g["steps"], chunk_steps=5)
+    x, hist = s.sample(c, g["steps"], top_k=g["top_k"], top_p=g["top_p"], temperature=g["temperature"],
+                       best_in_first=g["best_in_first"], mask_invalid=g["masks"][0], mask_invalid_completion=g["masks"][1],
+                       noise=noise, use_graph=use_graph)
+    x = x.cpu()
+    assert x.shape == g["tokens"].shape, (x.shape, g["tokens"].shape)   # incl. early termination at the same step
+    assert torch.equal(x, g["tokens"])
+    util.check_history_summary(x, hist, g["hist"])
+
+
+@pytest.mark.parametrize("B,Lc,steps,masks,chunk", [(5, 1, 6, (True, False), 32), (2, 40, 23, (False, False), 7),
+                                                    (7, 17, 9, (True, True), 4)])
+def test_sampler_matches_oracle(cuda, B, Lc, steps, masks, chunk):
+    """Distinct conditioning per row, L_cond = 1 (unconditional start), ragged chunking; full logits history compared."""
+    cfg = dict(synth.TINY_GPT, n_layers=(3, 2))
+    sd = synth.gpt_state_dict(cfg, seed=21, peaky=True)
+    c = synth.cond_indices(B, Lc, seed=4) if Lc > 1 else torch.tensor([[list(END)]]).repeat(B, 1, 1)
+    noise = util.noise_from_seed(5, steps, B, 4097)
+    ox, oh = O.sample_indices(sd, O.GPTSpec(**cfg), c, c[:, :0], steps, END, True, 30, 0.7, 1.0, masks[0], masks[1],
+                              noise=O.ListNoise(noise.reshape(-1, B, 4097)), cached=True)
+    s = make_sampler(cuda, cfg, sd, B, Lc, steps, chunk_steps=chunk, prefill_tokens=3 * max(Lc, 1))
+    for use_graph in (False, True):
+        x, hist = s.sample(c, steps, top_k=30, top_p=0.7, best_in_first=True, mask_invalid=masks[0],
+                           mask_invalid_completion=masks[1], noise=noise, use_graph=use_graph)
+        assert torch.equal(x.cpu(), ox)
+        for a, b in zip(hist, oh):
+            a = a.cpu()
+            assert torch.equal(torch.isfinite(a), torch.isfinite(b))
+            fin = torch.isfinite(b)
+            assert (a[fin] - b[fin]).abs().max() < 5e-5
+
+
+def test_sampler_device_rng_is_the_multinomial_stream(cuda):
+    """Without explicit noise the sampler draws Exp(1) with the same torch call torch.multinomial uses, so a re-seeded run
+    repeats itself and equals a run fed with the tensor drawn by hand."""
+    cfg = synth.TINY_GPT
+    sd = synth.gpt_state_dict(cfg, seed=8, peaky=True)
+    B, Lc, steps = 3, 10, 6
+    c = synth.cond_indices(B, Lc, seed=1)
+    s = make_sampler(cuda, cfg, sd, B, Lc, steps)
+    torch.manual_seed(123); torch.cuda.manual_seed(123)
+    x1, _ = s.sample(c, steps, top_k=50, top_p=0.0, mask_invalid=False, stop_early=False)
+    x1 = x1.clone()
+    torch.manual_seed(123); torch.cuda.manual_seed(123)
+    noise = torch.stack([torch.stack([torch.empty(B, 4097, device=cuda).exponential_(1.0) for _ in range(4)])
+                         for _ in range(steps)])
+    x2, _ = s.sample(c, steps, top_k=50, top_p=0.0, mask_invalid=False, noise=noise, stop_early=False)
+    assert torch.equal(x1, x2)
+
+
+def test_decoder_golden_and_oracle(cuda):
+    g = torch.load(util.GOLDEN + "/decoder.pt")
+    sd = synth.vqdif_state_dict(seed=g["wseed"])
+    code = synth.code_grids(1, seed=g["code_seed"])
+    gen = torch.Generator().manual_seed(g["pts_seed"])
+    Xtg = torch.rand(1, g["n"], 3, generator=gen) * 2 - 1
+    dec = decoder.ImplicitDecoder(sd, cuda, impl=1)
+    out = dec.decode_index(code, Xtg)["logits"]
+    assert out.shape == (1, g["n"], 1)
+    err = (out[0, :, 0].cpu() - g["logits"]).abs().max().item()
+    assert err < 1e-4, err                     # north-star tolerance: 1e-4 fp32
+    occ = torch.sigmoid(out[0, :, 0].cpu())
+    assert (occ - torch.sigmoid(g["logits"])).abs().max() < 1e-4
+
+
+def test_decoder_pieces_vs_oracle(cuda):
+    sd = synth.vqdif_state_dict(seed=6)
+    dec = decoder.ImplicitDecoder(sd, cuda, impl=1)
+    code = synth.code_grids(2, seed=1)
+    # get_code: exact
+    assert torch.equal(dec.get_code(code).cpu(), O.get_code(sd, code))
+    # per-point kernel on an oracle-made feature grid (isolates the fused trilinear + MLP kernel), incl. out-of-range points
+    grid = O.feature_grid(sd, code)
+    gen = torch.Generator().manual_seed(2)
+    Xtg = torch.rand(2, 5000, 3, generator=gen) * 2.6 - 1.3
+    Xtg[:, :4] = torch.tensor([[-1., -1, -1], [1, 1, 1], [1.101, 1.101, 1.101], [-1.101, 0, 1.2]])
+    ref = O.decode_points(sd, grid, Xtg)[..., 0]
+    gcl = grid.permute(0, 2, 3, 4, 1).contiguous().to(cuda)
+    out = dec.decode_points(gcl, Xtg).cpu()
+    assert (out - ref).abs().max() < 2e-5
+    # shared query set (stride 0) == per-shape copies
+    out_shared = dec.decode_points(gcl, Xtg[:1]).cpu()
+    assert torch.equal(out_shared[1], dec.decode_points(gcl[1:], Xtg[:1]).cpu()[0])
+    # layout kernel
+    g2 = torch.randn(2, 32, 4, 5, 6)
+    cl = torch.empty(2, 4, 5, 6, 32, device=cuda)
+    from shapeformer_b200 import _lib
+    _lib.check(_lib.load().sfb200_grid_to_channels_last(_lib.ptr(g2.to(cuda)), _lib.ptr(cl), 2, 32, 120, _lib.stream_ptr()))
+    assert torch.equal(cl.cpu(), g2.permute(0, 2, 3, 4, 1).contiguous())
+
+
+def test_tokens_to_dense(cuda):
+    sd = synth.vqdif_state_dict(seed=6)
+    dec = decoder.ImplicitDecoder(sd, cuda, impl=1)
+    g = torch.Generator().manual_seed(0)
+    toks = torch.stack([torch.randint(0, 4097, (3, 40), generator=g), torch.randint(0, 4097, (3, 40), generator=g)], -1)
+    toks[1, 5:] = 4096
+    toks[2, 3, 0] = toks[2, 1, 0]   # duplicate position: the later tuple wins
+    empty = torch.tensor([7, 4000, 0])
+    out = dec.tokens_to_dense(toks, empty).cpu()
+    for b in range(3):
+        assert torch.equal(out[b], O.tokens_to_dense(toks[b], empty[b]))
+
+
+def test_full_64cubed_decode_properties(cuda):
+    """BASELINE size (262,144 query points): size-independent checks — a shape decoded alone equals the same shape inside a
+    batch, and a random 4,096-point subset matches the oracle."""
+    sd = synth.vqdif_state_dict(seed=6)
+    dec = decoder.ImplicitDecoder(sd, cuda, impl=1)
+    code = synth.code_grids(2, seed=5)
+    Xtg = synth.make_grid(64)[None]
+    full = dec.decode_index(code, Xtg)["logits"]
+    assert full.shape == (2, 64 ** 3, 1)
+    alone = dec.decode_index(code[1:], Xtg)["logits"]
+    assert (full[1] - alone[0]).abs().max() < 1e-5     # cuDNN may pick another algorithm for B=1; MLP kernel is bitwise
+    sel = torch.randperm(64 ** 3, generator=torch.Generator().manual_seed(1))[:4096]
+    ref = O.decode_index(sd, code[:1], Xtg[:, sel])["logits"]
+    assert (full[0, sel.to(cuda)].cpu() - ref[0]).abs().max() < 1e-4

@@ -1,0 +1,141 @@
+"""GPU parity: every libsfb200 operator against the CPU oracle on the same seeded inputs (called through the C-ABI)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import sf_oracle as O
+from shapeformer_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 64, 128), (5, 1024, 1024), (16, 3072, 1024), (17, 4097, 1024), (33, 1024, 4096),
+                                   (64, 4096, 1024), (64, 4097, 1024), (200, 384, 128), (1000, 1024, 1024), (64, 128, 512)])
+@pytest.mark.parametrize("mode", ["plain", "bias_gelu", "bias_res"])
+def test_linear(cuda, M, N, K, mode):
+    x, W, b, r = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05), rnd(N, seed=3), rnd(M, N, seed=4)
+    if mode == "plain":
+        ref = F.linear(x, W)
+        out = ops.linear(x.to(cuda), W.to(cuda))
+    elif mode == "bias_gelu":
+        ref = F.gelu(F.linear(x, W, b))
+        out = ops.linear(x.to(cuda), W.to(cuda), b.to(cuda), act="gelu")
+    else:
+        ref = r + F.linear(x, W, b)
+        out = ops.linear(x.to(cuda), W.to(cuda), b.to(cuda), residual=r.to(cuda))
+    err = (out.cpu() - ref).abs().max().item()
+    assert err < 2e-5 * max(1.0, ref.abs().max().item()), err
+
+
+def test_linear_in_place_residual_and_determinism(cuda):
+    x, W, b = rnd(64, 1024, seed=1).to(cuda), rnd(1024, 1024, seed=2, scale=0.03).to(cuda), rnd(1024, seed=3).to(cuda)
+    r = rnd(64, 1024, seed=4).to(cuda)
+    a = ops.linear(x, W, b, residual=r)
+    for _ in range(3):
+        assert torch.equal(a, ops.linear(x, W, b, residual=r))   # cluster split-K sums in rank order: bitwise stable
+
+
+@pytest.mark.parametrize("rows,d", [(1, 128), (64, 1024), (777, 1024)])
+def test_layernorm(cuda, rows, d):
+    x, w, b = rnd(rows, d, seed=1, scale=3.0) + 0.5, rnd(d, seed=2) + 1, rnd(d, seed=3)
+    out = ops.layernorm(x.to(cuda), w.to(cuda), b.to(cuda)).cpu()
+    assert (out - F.layer_norm(x, (d,), w, b, 1e-5)).abs().max() < 1e-5
+
+
+def _ref_attn(q, K, V):
+    """q (B,H,hd), K/V (B,H,T,hd) -> (B,H*hd) exactly as CausalSelfAttention for the newest query."""
+    att = (q[:, :, None] @ K.transpose(-2, -1)) * (1.0 / math.sqrt(q.shape[-1]))
+    return (F.softmax(att, -1) @ V)[:, :, 0].reshape(q.shape[0], -1)
+
+
+@pytest.mark.parametrize("B,H,pos,n_split", [(1, 2, 0, 1), (3, 2, 1, 1), (2, 16, 7, 1), (2, 4, 100, 3), (1, 16, 511, 8),
+                                              (64, 16, 300, 1), (2, 2, 37, 8)])
+def test_attn_decode(cuda, B, H, pos, n_split):
+    max_len, d = 520, H * 64
+    qkv = rnd(B, 3 * d, seed=1)
+    Kc, Vc = rnd(B, H, max_len, 64, seed=2), rnd(B, H, max_len, 64, seed=3)
+    kc, vc = Kc.to(cuda), Vc.to(cuda)
+    out = ops.attn_decode(qkv.to(cuda), kc, vc, pos, n_split).cpu()
+    q, k, v = (qkv[:, i * d:(i + 1) * d].view(B, H, 64) for i in range(3))
+    Kr, Vr = Kc.clone(), Vc.clone()
+    Kr[:, :, pos], Vr[:, :, pos] = k, v
+    ref = _ref_attn(q, Kr[:, :, :pos + 1], Vr[:, :, :pos + 1])
+    assert (out - ref).abs().max() < 2e-5
+    assert torch.equal(kc.cpu(), Kr) and torch.equal(vc.cpu(), Vr)   # append only touched `pos`
+
+
+@pytest.mark.parametrize("B,H,T", [(1, 2, 1), (2, 2, 9), (2, 16, 64), (3, 4, 255)])
+def test_attn_prefill(cuda, B, H, T):
+    max_len, d = 300, H * 64
+    qkv = rnd(B, T, 3 * d, seed=5)
+    kc, vc = torch.zeros(B, H, max_len, 64, device=cuda), torch.zeros(B, H, max_len, 64, device=cuda)
+    out = ops.attn_prefill(qkv.to(cuda), kc, vc).cpu()
+    q, k, v = (qkv[..., i * d:(i + 1) * d].view(B, T, H, 64).transpose(1, 2) for i in range(3))
+    att = (q @ k.transpose(-2, -1)) / 8.0
+    att = att.masked_fill(torch.triu(torch.ones(T, T, dtype=torch.bool), 1), float("-inf"))
+    ref = (F.softmax(att, -1) @ v).transpose(1, 2).reshape(B, T, d)
+    assert (out - ref).abs().max() < 2e-5
+    assert torch.equal(kc[:, :, :T].cpu(), k.contiguous()) and torch.equal(vc[:, :, :T].cpu(), v.contiguous())
+    assert float(kc[:, :, T:].abs().max()) == 0.0 if T < max_len else True
+
+
+SAMPLE_CASES = [(100, 0.4, 1.0, True, True, True), (50, 0.0, 1.0, True, False, False), (1, 0.001, 1.0, False, False, False),
+                (0, 0.9, 0.7, False, True, False), (5000, 1.0, 1.3, False, True, True), (0, 0.0, 1.0, False, False, False),
+                (3, 0.5, 2.0, True, True, True)]
+
+
+@pytest.mark.parametrize("top_k,top_p,T,bif,mi,mic", SAMPLE_CASES)
+@pytest.mark.parametrize("tuple_i", [0, 1])
+def test_ar_sample_bit_exact(cuda, top_k, top_p, T, bif, mi, mic, tuple_i):
+    """mask -> filter -> draw: tokens identical to the oracle (= the reference's sampling_masker + sample_logits) for the
+    same logits and noise; masked logits identical bit for bit."""
+    B, V, Lc, L, max_len = 9, 4097, 6, 9, 16
+    g = torch.Generator().manual_seed(top_k * 7 + tuple_i)
+    logits = torch.randn(B, V, generator=g) * 2.5
+    logits[4, :70] = logits[4, 70]                   # a tie group
+    tokens = torch.zeros(B, max_len, 2, dtype=torch.int64)
+    tokens[:, :Lc] = synth.cond_indices(B, Lc, seed=9)
+    for b in range(B):                                # three generated tuples, increasing positions
+        p = torch.sort(torch.randint(0, 4000, (3,), generator=g))[0] + torch.arange(3)
+        tokens[b, Lc:L, 0], tokens[b, Lc:L, 1] = p, torch.randint(0, 4096, (3,), generator=g)
+    tokens[2, L - 1, 0] = 4096                        # a row that already ended
+    if tuple_i == 1:
+        tokens[:, L, 0] = torch.randint(0, 4096, (B,), generator=g)
+        tokens[5, L, 0] = 4096                        # forced end value
+    qs, qb = torch.empty(B, V).exponential_(1.0, generator=g), torch.empty(B, V).exponential_(1.0, generator=g)
+    # oracle
+    masked = O.sampling_masker(logits, tokens[:, :L + 1], Lc, L - Lc, tuple_i, (4096, 4096), mi, mic)
+    new = O.sample_rows(masked, qs, top_k, top_p, T)
+    best = O.sample_rows(masked, qb, 1, 0.001, T)
+    if bif:
+        new[0] = best[0]
+    tk = tokens.to(cuda)
+    hist = ops.ar_sample(logits.to(cuda), tk, L, Lc, tuple_i, qs.to(cuda), qb.to(cuda), (4096, 4096), top_k, top_p, T, bif,
+                         mi, mic)
+    got = tk[:, L, tuple_i].cpu()
+    assert torch.equal(hist.cpu(), masked)
+    assert torch.equal(got, new), (got.tolist(), new.tolist())
+    untouched = tk.cpu().clone()
+    untouched[:, L, tuple_i] = tokens[:, L, tuple_i]
+    assert torch.equal(untouched, tokens)
+
+
+def test_ar_sample_small_vocab(cuda):
+    B, V = 4, 37
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(B, V, generator=g)
+    tokens = torch.zeros(B, 8, 2, dtype=torch.int64)
+    tokens[:, 0] = torch.tensor([36, 36])
+    qs, qb = torch.empty(B, V).exponential_(1.0, generator=g), torch.empty(B, V).exponential_(1.0, generator=g)
+    masked = O.sampling_masker(logits, tokens[:, :2], 1, 0, 0, (36, 36), True, False)
+    new = O.sample_rows(masked, qs, 5, 0.9, 1.0)
+    tk = tokens.to(cuda)
+    ops.ar_sample(logits.to(cuda), tk, 1, 1, 0, qs.to(cuda), qb.to(cuda), (36, 36), 5, 0.9, 1.0, False, True, False)
+    assert torch.equal(tk[:, 1, 0].cpu(), new)
