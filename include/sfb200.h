@@ -33,6 +33,8 @@ extern "C" {
 int sfb200_version(void);
 const char *sfb200_error_string(int code);
 const char *sfb200_last_cuda_error(void);
+/* Number of kernels this library has launched in this process (a graph replay counts every kernel node it contains). */
+int64_t sfb200_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * VQDIF decoder side  (vqdif/vqdif.py:60-76, vqdif/dec.py:62-100, vqdif/quantizer.py:19-30)
@@ -62,9 +64,10 @@ int sfb200_decoder_set_weights(const float *mlp_weights, void *stream);
  *   grid   (B, R, R, R, 32) fp32 channel-last feature grid (output of UNet3D+Upsampler),
  *   xtg    (B or 1, N, 3) fp32 query points in [-1,1]; xtg_batch_stride = N*3 or 0 when shared by all shapes,
  *   logits (B, N) fp32 occupancy logits (the reference's (B,N,1)).
- * impl: 0 = default (tcgen05 split-bf16 tensor-core kernel), 1 = fp32 FFMA kernel (verification / small N). */
+ * impl: 0 = default (tcgen05 split-bf16 tensor-core kernel), 1 = fp32 FFMA kernel (verification / small N).
+ * sigmoid != 0 writes occupancy = 1/(1+exp(-logit)) instead (decode_sample_indices, shapeformer/shapeformer.py:388). */
 int sfb200_decoder_points(const float *grid, const float *xtg, int64_t xtg_batch_stride, float *logits, int B, int R,
-                          int64_t N, int impl, void *stream);
+                          int64_t N, int impl, int sigmoid, void *stream);
 
 /* filter_end_tokens + batch_sparse2dense (shapeformer/common.py:50-55,171-189; caller shapeformer/shapeformer.py:342-351):
  * dense[b][:] = empty_index[b]; for t in order: if pos,val are not end tokens: dense[b][pos] = val (later writes win).
@@ -160,6 +163,13 @@ int sfb200_ar_steps(sfb200_ar *h, int n_steps, const float *noise, int use_graph
 /* Device-side status words the caller may copy back after a sync: status[0] = steps done, status[1] = first step index
  * (0-based) at which all rows had ended, or -1.  Returns a device pointer to int32[4]. */
 const int32_t *sfb200_ar_status_ptr(const sfb200_ar *h);
+
+/* Measurement aid for bench.py: when enabled (eager stepping only), every attention launch of sfb200_ar_steps is bracketed
+ * by CUDA events on `stream`.  sfb200_ar_profile_read must be called after the stream has been synchronised; it returns the
+ * summed device time (ms), the number of launches and the ALGORITHMIC bytes of those launches
+ * (per launch: B * [2*pos*d*4 (K,V read) + 2*d*4 (append) + 2*d*4 (q in, out)]) and resets the counters. */
+int sfb200_ar_profile(sfb200_ar *h, int enable);
+int sfb200_ar_profile_read(sfb200_ar *h, double *attn_ms, int64_t *attn_launches, double *attn_bytes);
 
 /* ---- individual AR operators (exposed for parity tests and profiling; the same kernels the calls above enqueue) ---- */
 

@@ -42,11 +42,12 @@ SIGNATURES = {
     "sfb200_version": (ctypes.c_int, []),
     "sfb200_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "sfb200_last_cuda_error": (ctypes.c_char_p, []),
+    "sfb200_launch_count": (ctypes.c_int64, []),
     "sfb200_code_gather": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
     "sfb200_grid_to_channels_last": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int64, vp]),
     "sfb200_decoder_set_weights": (ctypes.c_int, [vp, vp]),
     "sfb200_decoder_points": (ctypes.c_int, [vp, vp, ctypes.c_int64, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int64,
-                                             ctypes.c_int, vp]),
+                                             ctypes.c_int, ctypes.c_int, vp]),
     "sfb200_tokens_to_dense": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64,
                                               ctypes.c_int64, vp]),
     "sfb200_ar_weight_floats": (ctypes.c_int64, [ctypes.POINTER(ArConfig)]),
@@ -59,6 +60,9 @@ SIGNATURES = {
     "sfb200_ar_begin": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ArSampling), vp]),
     "sfb200_ar_steps": (ctypes.c_int, [vp, ctypes.c_int, vp, ctypes.c_int, vp]),
     "sfb200_ar_status_ptr": (vp, [vp]),
+    "sfb200_ar_profile": (ctypes.c_int, [vp, ctypes.c_int]),
+    "sfb200_ar_profile_read": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
+                                              ctypes.POINTER(ctypes.c_double)]),
     "sfb200_linear": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
     "sfb200_layernorm": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp]),
     "sfb200_attn_decode": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,

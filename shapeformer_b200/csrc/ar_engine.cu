@@ -4,6 +4,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "ar_kernels.cuh"
 
 namespace sfb {
@@ -131,6 +133,14 @@ struct sfb200_ar {
     const float *g_noise;
     int g_B;
     sfb200_ar_sampling g_sp;
+    long long g_nodes;         // kernel nodes in the captured step
+    bool capturing;
+    // attention profiling (bench.py roofline): events bracketing every attention launch of eager steps
+    bool prof;
+    std::vector<cudaEvent_t> *ev;
+    size_t ev_used;
+    double prof_bytes;
+    int steps_host;            // steps enqueued since sfb200_ar_begin (host mirror of st[ST_STEPS])
 };
 
 static inline const float *W_(const sfb200_ar *h, int id, int g, int l) { return h->w + weight_offset(&h->lay, id, g, l); }
@@ -206,6 +216,10 @@ void sfb200_ar_destroy(sfb200_ar *h) {
     if (!h) return;
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+    if (h->ev) {
+        for (cudaEvent_t e : *h->ev) cudaEventDestroy(e);
+        delete h->ev;
+    }
     free(h);
 }
 
@@ -235,8 +249,26 @@ static int block_step(sfb200_ar *h, int g, int l, float *x, cudaStream_t s) {
     float *ff = WS_<float>(h, h->buf.ff), *part = WS_<float>(h, h->buf.part);
     SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN1_W, g, l), W_(h, SFB200_W_LN1_B, g, l), hb, B, d, s));
     SFB_TRY(launch_linear(hb, W_(h, SFB200_W_QKV_W, g, l), W_(h, SFB200_W_QKV_B, g, l), nullptr, qkv, B, 3 * d, d, 0, s));
+    const bool timed = h->prof && !h->capturing;
+    if (timed) {
+        if (!h->ev) h->ev = new std::vector<cudaEvent_t>();
+        while (h->ev->size() < h->ev_used + 2) {
+            cudaEvent_t e;
+            SFB_CUDA_TRY(cudaEventCreate(&e));
+            h->ev->push_back(e);
+        }
+        SFB_CUDA_TRY(cudaEventRecord((*h->ev)[h->ev_used], s));
+    }
     SFB_TRY(launch_attn_decode(qkv, kcache(h, g, l, 0), vcache(h, g, l, 0), att, part, B, H, h->cfg.max_len, 0, st,
                                h->n_split, s));
+    if (timed) {
+        SFB_CUDA_TRY(cudaEventRecord((*h->ev)[h->ev_used + 1], s));
+        h->ev_used += 2;
+        // position of this launch = L-1: blocks[1] runs before the step's advance (L = L_cond + j), blocks[0] after it
+        // (L = L_cond + j + 1, and steps_host has already been incremented)
+        const double pos = (double)(h->L_cond + h->steps_host) - 1.0;
+        h->prof_bytes += (double)B * (2.0 * pos * d * 4.0 + 4.0 * d * 4.0);
+    }
     SFB_TRY(launch_linear(att, W_(h, SFB200_W_PROJ_W, g, l), W_(h, SFB200_W_PROJ_B, g, l), x, x, B, d, d, 0, s));
     SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN2_W, g, l), W_(h, SFB200_W_LN2_B, g, l), hb, B, d, s));
     SFB_TRY(launch_linear(hb, W_(h, SFB200_W_FC1_W, g, l), W_(h, SFB200_W_FC1_B, g, l), nullptr, ff, B, 4 * d, d, 1, s));
@@ -260,6 +292,7 @@ extern "C" int sfb200_ar_begin(sfb200_ar *h, int B, int L_cond, const sfb200_ar_
     const int d = h->cfg.n_embd;
     h->B = B; h->L_cond = L_cond; h->sp = *sp;
     h->n_split = pick_nsplit(B, h->cfg.n_head);
+    h->steps_host = 0;
     int32_t *st = WS_<int32_t>(h, h->buf.st);
     SFB_TRY(launch_state_init(st, L_cond, s));
     float *px = WS_<float>(h, h->buf.px), *px1 = WS_<float>(h, h->buf.px1), *x0 = WS_<float>(h, h->buf.x0);
@@ -312,6 +345,7 @@ static int enqueue_step(sfb200_ar *h, const float *noise, cudaStream_t s) {
     p.noise_sample = noise + 2 * draw; p.noise_best = noise + 3 * draw;
     SFB_TRY(launch_sample(p, s));
     SFB_TRY(launch_advance(st, h->tokens, B, h->cfg.max_len, p.end0, p.end1, s));
+    if (!h->capturing) h->steps_host += 1;
     // --- next position through blocks[0]
     SFB_TRY(launch_embed(h->tokens, W_(h, SFB200_W_TOK_EMB0, 0, 0), W_(h, SFB200_W_TOK_EMB1, 0, 0),
                          W_(h, SFB200_W_EXTRA_EMB, 0, 0), W_(h, SFB200_W_POS_EMB, 0, 0), W_(h, SFB200_W_COND_POS_EMB, 0, 0),
@@ -341,7 +375,12 @@ extern "C" int sfb200_ar_steps(sfb200_ar *h, int n_steps, const float *noise, in
             cudaGraph_t graph = nullptr;
             if (!h->cap_stream) SFB_CUDA_TRY(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
             SFB_CUDA_TRY(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+            h->capturing = true;
+            const long long before = sfb200_launch_count();
             const int r = enqueue_step(h, noise, h->cap_stream);
+            h->g_nodes = sfb200_launch_count() - before;
+            count_launches(-h->g_nodes);   // recorded, not executed
+            h->capturing = false;
             const cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
             if (r != SFB200_OK) { if (graph) cudaGraphDestroy(graph); return r; }
             SFB_CUDA_TRY(e);
@@ -350,9 +389,37 @@ extern "C" int sfb200_ar_steps(sfb200_ar *h, int n_steps, const float *noise, in
             SFB_CUDA_TRY(ei);
             h->g_noise = noise; h->g_B = h->B; h->g_sp = h->sp;
         }
-        for (; done < n_steps; ++done) SFB_CUDA_TRY(cudaGraphLaunch(h->gexec, s));
+        for (; done < n_steps; ++done) {
+            SFB_CUDA_TRY(cudaGraphLaunch(h->gexec, s));
+            count_launches(h->g_nodes);
+            h->steps_host += 1;
+        }
     } else {
         for (; done < n_steps; ++done) SFB_TRY(enqueue_step(h, noise, s));
     }
+    return SFB200_OK;
+}
+
+extern "C" int sfb200_ar_profile(sfb200_ar *h, int enable) {
+    if (!h) return SFB200_E_ARG;
+    h->prof = enable != 0;
+    h->ev_used = 0;
+    h->prof_bytes = 0.0;
+    return SFB200_OK;
+}
+
+extern "C" int sfb200_ar_profile_read(sfb200_ar *h, double *attn_ms, int64_t *attn_launches, double *attn_bytes) {
+    if (!h || !attn_ms || !attn_launches || !attn_bytes) return SFB200_E_ARG;
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+        float t = 0.f;
+        SFB_CUDA_TRY(cudaEventElapsedTime(&t, (*h->ev)[i], (*h->ev)[i + 1]));
+        ms += t;
+    }
+    *attn_ms = ms;
+    *attn_launches = (int64_t)(h->ev_used / 2);
+    *attn_bytes = h->prof_bytes;
+    h->ev_used = 0;
+    h->prof_bytes = 0.0;
     return SFB200_OK;
 }

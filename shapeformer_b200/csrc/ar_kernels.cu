@@ -311,6 +311,7 @@ static int launch_linear_t(const float *x, const float *W, const float *bias, co
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     SFB_CUDA_TRY(cudaLaunchKernelEx(&cfg, linear_kernel<MI, KSPLIT>, x, W, bias, residual, y, M, N, K, act));
+    count_launches(1);
     return SFB200_OK;
 }
 

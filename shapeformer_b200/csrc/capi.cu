@@ -5,7 +5,10 @@
 #include "ar_kernels.cuh"
 #include "decoder_kernels.cuh"
 
+#include <atomic>
 namespace sfb {
+static std::atomic<long long> g_launches{0};
+void count_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 static thread_local char g_err[512] = "";
 void set_cuda_error(cudaError_t e, const char *where) {
     snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
@@ -28,6 +31,7 @@ const char *sfb200_error_string(int code) {
     return "unknown error";
 }
 const char *sfb200_last_cuda_error(void) { return g_err; }
+int64_t sfb200_launch_count(void) { return (int64_t)g_launches.load(); }
 
 int sfb200_code_gather(const int64_t *code_ind, const float *codebook, float *out, int B, int cells, int C, int n_codes,
                        void *stream) {
@@ -44,10 +48,10 @@ int sfb200_decoder_set_weights(const float *mlp_weights, void *stream) {
     return decoder_set_weights_tc(mlp_weights, as_stream(stream));
 }
 int sfb200_decoder_points(const float *grid, const float *xtg, int64_t xtg_batch_stride, float *logits, int B, int R,
-                          int64_t N, int impl, void *stream) {
+                          int64_t N, int impl, int sigmoid, void *stream) {
     if (!grid || !xtg || !logits) return SFB200_E_ARG;
-    if (impl == 1) return launch_decoder_points_ffma(grid, xtg, xtg_batch_stride, logits, B, R, N, as_stream(stream));
-    if (impl == 0) return launch_decoder_points_tc(grid, xtg, xtg_batch_stride, logits, B, R, N, as_stream(stream));
+    if (impl == 1) return launch_decoder_points_ffma(grid, xtg, xtg_batch_stride, logits, B, R, N, sigmoid, as_stream(stream));
+    if (impl == 0) return launch_decoder_points_tc(grid, xtg, xtg_batch_stride, logits, B, R, N, sigmoid, as_stream(stream));
     return SFB200_E_ARG;
 }
 int sfb200_tokens_to_dense(const int64_t *tokens, const int64_t *empty_index, int64_t *dense, int B, int T, int cells,

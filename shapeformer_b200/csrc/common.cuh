@@ -9,6 +9,7 @@
 namespace sfb {
 
 void set_cuda_error(cudaError_t e, const char *where);
+void count_launches(long long n);
 
 // Returns SFB200_OK or SFB200_E_CUDA after recording the message.
 static inline int check_launch(const char *where) {
@@ -18,6 +19,7 @@ static inline int check_launch(const char *where) {
         set_cuda_error(e, where);
         return SFB200_E_CUDA;
     }
+    count_launches(1);
     return SFB200_OK;
 }
 

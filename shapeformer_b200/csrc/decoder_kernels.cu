@@ -113,7 +113,8 @@ __device__ __forceinline__ void mlp_block(const float (&c)[32], float (&net)[32]
 
 __global__ void __launch_bounds__(128) decoder_points_ffma_kernel(const float *__restrict__ grid,
                                                                   const float *__restrict__ xtg, int64_t xtg_bstride,
-                                                                  float *__restrict__ logits, int R, int64_t N) {
+                                                                  float *__restrict__ logits, int R, int64_t N,
+                                                                  int sigmoid) {
     const int b = blockIdx.y;
     const int64_t n = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (n >= N) return;
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(128) decoder_points_ffma_kernel(const float *_
     float out = c_mlp[OFF_BO];
 #pragma unroll
     for (int i = 0; i < 32; ++i) out = fmaf(c_mlp[OFF_WO + i], fmaxf(net[i], 0.f), out);
+    if (sigmoid) out = 1.0f / (1.0f + expf(-out));
     logits[(size_t)b * N + n] = out;
 }
 
@@ -194,9 +196,9 @@ int decoder_set_weights_ffma(const float *w, cudaStream_t s) {
     return SFB200_OK;
 }
 int launch_decoder_points_ffma(const float *grid, const float *xtg, int64_t xtg_bstride, float *logits, int B, int R,
-                               int64_t N, cudaStream_t s) {
+                               int64_t N, int sigmoid, cudaStream_t s) {
     if (B <= 0 || R < 2 || N <= 0) return SFB200_E_ARG;
-    decoder_points_ffma_kernel<<<dim3((unsigned)((N + 127) / 128), B), 128, 0, s>>>(grid, xtg, xtg_bstride, logits, R, N);
+    decoder_points_ffma_kernel<<<dim3((unsigned)((N + 127) / 128), B), 128, 0, s>>>(grid, xtg, xtg_bstride, logits, R, N, sigmoid);
     return check_launch("decoder_points_ffma");
 }
 

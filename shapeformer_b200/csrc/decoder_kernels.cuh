@@ -9,9 +9,9 @@ int launch_tokens_to_dense(const int64_t *tokens, const int64_t *empty, int64_t 
                            int64_t end_pos, int64_t end_val, cudaStream_t s);
 int decoder_set_weights_ffma(const float *w, cudaStream_t s);
 int launch_decoder_points_ffma(const float *grid, const float *xtg, int64_t xtg_bstride, float *logits, int B, int R,
-                               int64_t N, cudaStream_t s);
+                               int64_t N, int sigmoid, cudaStream_t s);
 // tcgen05 path (decoder_tc.cu)
 int decoder_set_weights_tc(const float *w, cudaStream_t s);
 int launch_decoder_points_tc(const float *grid, const float *xtg, int64_t xtg_bstride, float *logits, int B, int R,
-                             int64_t N, cudaStream_t s);
+                             int64_t N, int sigmoid, cudaStream_t s);
 }  // namespace sfb

@@ -105,8 +105,8 @@ class ImplicitDecoder:
                    "grid_to_channels_last")
         return out
 
-    def decode_points(self, grid_cl, Xtg, impl=None):
-        """grid_cl (B,R,R,R,32), Xtg (B or 1, N, 3) in [-1,1] -> logits (B, N)."""
+    def decode_points(self, grid_cl, Xtg, impl=None, sigmoid=False):
+        """grid_cl (B,R,R,R,32), Xtg (B or 1, N, 3) in [-1,1] -> logits (B, N) (occupancy when sigmoid=True)."""
         B, R = grid_cl.shape[0], grid_cl.shape[1]
         if grid_cl.shape[-1] != 32 or grid_cl.shape[2] != R or grid_cl.shape[3] != R:
             raise _lib.Sfb200Error("feature grid must be (B,R,R,R,32)")
@@ -120,7 +120,8 @@ class ImplicitDecoder:
         out = torch.empty(B, N, dtype=torch.float32, device=self.device)
         self._activate()
         _lib.check(self.lib.sfb200_decoder_points(_lib.ptr(grid_cl), _lib.ptr(x), stride, _lib.ptr(out), B, R, N,
-                                                  self.impl if impl is None else impl, _lib.stream_ptr()),
+                                                  self.impl if impl is None else impl, int(bool(sigmoid)),
+                                                  _lib.stream_ptr()),
                    "decoder_points")
         return out
 
@@ -131,6 +132,11 @@ class ImplicitDecoder:
     def decode_index(self, code_ind, Xtg, impl=None):
         """VQDIF.decode_index (vqdif/vqdif.py:74-76)."""
         return self.decode(self.get_code(code_ind), Xtg, impl)
+
+    def occupancy(self, code_ind, Xtg, impl=None):
+        """decode_index followed by the sigmoid of decode_sample_indices (shapeformer/shapeformer.py:382-391), batched:
+        (B,R,R,R) int64 codes -> (B, N) occupancy in [0,1]."""
+        return self.decode_points(self.feature_grid(self.get_code(code_ind)), Xtg, impl, sigmoid=True)
 
     def tokens_to_dense(self, tokens, empty_index, res=16, end_tokens=(4096, 4096)):
         """filter_end_tokens + batch_sparse2dense for every row (shapeformer/common.py:50-55,171-189):
