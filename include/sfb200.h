@@ -178,6 +178,11 @@ int sfb200_ar_profile_read(sfb200_ar *h, double *attn_ms, int64_t *attn_launches
 int sfb200_linear(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
                   int act, void *stream);
 
+/* Same contract as sfb200_linear on the tcgen05 tensor cores with fp32-level accuracy: operands split into two TF32 parts,
+ * three MMAs per product, TMEM accumulator promoted to fp32 registers every two K chunks, cluster (DSMEM) split-K. */
+int sfb200_linear_tc(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
+                     int act, void *stream);
+
 /* LayerNorm over the last dim, eps = 1e-5 (mingpt.py:97-98,224). */
 int sfb200_layernorm(const float *x, const float *w, const float *b, float *y, int rows, int d, void *stream);
 

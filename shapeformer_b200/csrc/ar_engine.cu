@@ -227,17 +227,25 @@ const int32_t *sfb200_ar_status_ptr(const sfb200_ar *h) { return h ? WS_<int32_t
 
 }  // extern "C"
 
+// nn.Linear dispatch: tcgen05 3xTF32 kernel for M >= 9 rows, fp32 FFMA kernel for the smallest batches.
+static int linear(sfb200_ar *h, const float *x, const float *W, const float *bias, const float *residual, float *y, int M,
+                  int N, int K, int act, cudaStream_t s) {
+    if (M >= 9)
+        return launch_linear_tc(x, W, bias, residual, y, M, N, K, act, s);
+    return launch_linear(x, W, bias, residual, y, M, N, K, act, s);
+}
+
 // One transformer block over M = rows*T positions (prefill) — Block.forward, transformer/mingpt.py:108-111.
 static int block_prefill(sfb200_ar *h, int g, int l, float *x, int row0, int rows, int T, cudaStream_t s) {
     const int d = h->cfg.n_embd, H = h->cfg.n_head, M = rows * T;
     float *ph = WS_<float>(h, h->buf.ph), *pqkv = WS_<float>(h, h->buf.pqkv), *pff = WS_<float>(h, h->buf.pff);
     SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN1_W, g, l), W_(h, SFB200_W_LN1_B, g, l), ph, M, d, s));
-    SFB_TRY(launch_linear(ph, W_(h, SFB200_W_QKV_W, g, l), W_(h, SFB200_W_QKV_B, g, l), nullptr, pqkv, M, 3 * d, d, 0, s));
+    SFB_TRY(linear(h, ph, W_(h, SFB200_W_QKV_W, g, l), W_(h, SFB200_W_QKV_B, g, l), nullptr, pqkv, M, 3 * d, d, 0, s));
     SFB_TRY(launch_attn_prefill(pqkv, kcache(h, g, l, row0), vcache(h, g, l, row0), ph, rows, H, T, h->cfg.max_len, s));
-    SFB_TRY(launch_linear(ph, W_(h, SFB200_W_PROJ_W, g, l), W_(h, SFB200_W_PROJ_B, g, l), x, x, M, d, d, 0, s));
+    SFB_TRY(linear(h, ph, W_(h, SFB200_W_PROJ_W, g, l), W_(h, SFB200_W_PROJ_B, g, l), x, x, M, d, d, 0, s));
     SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN2_W, g, l), W_(h, SFB200_W_LN2_B, g, l), ph, M, d, s));
-    SFB_TRY(launch_linear(ph, W_(h, SFB200_W_FC1_W, g, l), W_(h, SFB200_W_FC1_B, g, l), nullptr, pff, M, 4 * d, d, 1, s));
-    SFB_TRY(launch_linear(pff, W_(h, SFB200_W_FC2_W, g, l), W_(h, SFB200_W_FC2_B, g, l), x, x, M, d, 4 * d, 0, s));
+    SFB_TRY(linear(h, ph, W_(h, SFB200_W_FC1_W, g, l), W_(h, SFB200_W_FC1_B, g, l), nullptr, pff, M, 4 * d, d, 1, s));
+    SFB_TRY(linear(h, pff, W_(h, SFB200_W_FC2_W, g, l), W_(h, SFB200_W_FC2_B, g, l), x, x, M, d, 4 * d, 0, s));
     return SFB200_OK;
 }
 
@@ -248,7 +256,7 @@ static int block_step(sfb200_ar *h, int g, int l, float *x, cudaStream_t s) {
     float *hb = WS_<float>(h, h->buf.h), *qkv = WS_<float>(h, h->buf.qkv), *att = WS_<float>(h, h->buf.att);
     float *ff = WS_<float>(h, h->buf.ff), *part = WS_<float>(h, h->buf.part);
     SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN1_W, g, l), W_(h, SFB200_W_LN1_B, g, l), hb, B, d, s));
-    SFB_TRY(launch_linear(hb, W_(h, SFB200_W_QKV_W, g, l), W_(h, SFB200_W_QKV_B, g, l), nullptr, qkv, B, 3 * d, d, 0, s));
+    SFB_TRY(linear(h, hb, W_(h, SFB200_W_QKV_W, g, l), W_(h, SFB200_W_QKV_B, g, l), nullptr, qkv, B, 3 * d, d, 0, s));
     const bool timed = h->prof && !h->capturing;
     if (timed) {
         if (!h->ev) h->ev = new std::vector<cudaEvent_t>();
@@ -269,10 +277,10 @@ static int block_step(sfb200_ar *h, int g, int l, float *x, cudaStream_t s) {
         const double pos = (double)(h->L_cond + h->steps_host) - 1.0;
         h->prof_bytes += (double)B * (2.0 * pos * d * 4.0 + 4.0 * d * 4.0);
     }
-    SFB_TRY(launch_linear(att, W_(h, SFB200_W_PROJ_W, g, l), W_(h, SFB200_W_PROJ_B, g, l), x, x, B, d, d, 0, s));
+    SFB_TRY(linear(h, att, W_(h, SFB200_W_PROJ_W, g, l), W_(h, SFB200_W_PROJ_B, g, l), x, x, B, d, d, 0, s));
     SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN2_W, g, l), W_(h, SFB200_W_LN2_B, g, l), hb, B, d, s));
-    SFB_TRY(launch_linear(hb, W_(h, SFB200_W_FC1_W, g, l), W_(h, SFB200_W_FC1_B, g, l), nullptr, ff, B, 4 * d, d, 1, s));
-    SFB_TRY(launch_linear(ff, W_(h, SFB200_W_FC2_W, g, l), W_(h, SFB200_W_FC2_B, g, l), x, x, B, d, 4 * d, 0, s));
+    SFB_TRY(linear(h, hb, W_(h, SFB200_W_FC1_W, g, l), W_(h, SFB200_W_FC1_B, g, l), nullptr, ff, B, 4 * d, d, 1, s));
+    SFB_TRY(linear(h, ff, W_(h, SFB200_W_FC2_W, g, l), W_(h, SFB200_W_FC2_B, g, l), x, x, B, d, 4 * d, 0, s));
     return SFB200_OK;
 }
 
@@ -280,7 +288,7 @@ static int head(sfb200_ar *h, int g, const float *x, float *logits, int rows, cu
     const int d = h->cfg.n_embd;
     float *hb = WS_<float>(h, h->buf.h);
     SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_HEAD_LN_W, g, 0), W_(h, SFB200_W_HEAD_LN_B, g, 0), hb, rows, d, s));
-    SFB_TRY(launch_linear(hb, W_(h, SFB200_W_HEAD_W, g, 0), nullptr, nullptr, logits, rows, h->cfg.vocab[g], d, 0, s));
+    SFB_TRY(linear(h, hb, W_(h, SFB200_W_HEAD_W, g, 0), nullptr, nullptr, logits, rows, h->cfg.vocab[g], d, 0, s));
     return SFB200_OK;
 }
 

@@ -338,9 +338,73 @@ int pick_ksplit(int M, int N, int K, int MT) {
 int launch_linear(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
                   int act, cudaStream_t stream) {
     if (M <= 0 || N <= 0 || K <= 0 || K % LIN_BK != 0) return SFB200_E_ARG;
+    if (M <= 4) return launch_gemv(x, W, bias, residual, y, M, N, K, act, stream);
     if (M <= 16) return launch_linear_m<1>(x, W, bias, residual, y, M, N, K, act, pick_ksplit(M, N, K, 16), stream);
     if (M <= 32) return launch_linear_m<2>(x, W, bias, residual, y, M, N, K, act, pick_ksplit(M, N, K, 32), stream);
     return launch_linear_m<4>(x, W, bias, residual, y, M, N, K, act, pick_ksplit(M, N, K, 64), stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// GEMV-style linear for M <= 4 activation rows (single-shape latency runs): pure weight streaming.  One warp per output
+// feature: lanes stride the K dimension with 128-bit loads (all of a row's loads are issued before use), the M activation
+// rows are read through L1, and a shuffle reduction finishes each dot product.  fp32 FFMA, deterministic order.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int MR>
+__global__ void __launch_bounds__(256) gemv_kernel(const float *__restrict__ x, const float *__restrict__ W,
+                                                   const float *__restrict__ bias, const float *residual, float *y, int N,
+                                                   int K, int act) {
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const float *wr = W + (size_t)n * K;
+    float acc[MR];
+#pragma unroll
+    for (int m = 0; m < MR; ++m) acc[m] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 1024) {
+        float4 wv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int k = k0 + i * 128 + lane * 4;
+            wv[i] = k < K ? ld4_stream(wr + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int k = k0 + i * 128 + lane * 4;
+            if (k < K) {
+#pragma unroll
+                for (int m = 0; m < MR; ++m) {
+                    const float4 xv = ld4(x + (size_t)m * K + k);
+                    float a = acc[m];
+                    a = fmaf(wv[i].x, xv.x, a); a = fmaf(wv[i].y, xv.y, a);
+                    a = fmaf(wv[i].z, xv.z, a); a = fmaf(wv[i].w, xv.w, a);
+                    acc[m] = a;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MR; ++m) {
+        float v = warp_sum(acc[m]);
+        if (lane == 0) {
+            if (bias) v += bias[n];
+            if (act == 1) v = gelu_erf(v);
+            if (residual) v += residual[(size_t)m * N + n];
+            y[(size_t)m * N + n] = v;
+        }
+    }
+}
+
+int launch_gemv(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
+                int act, cudaStream_t s) {
+    if (M < 1 || M > 4 || K % 4 != 0) return SFB200_E_ARG;
+    const dim3 grid((N + 7) / 8);
+    switch (M) {
+        case 1: gemv_kernel<1><<<grid, 256, 0, s>>>(x, W, bias, residual, y, N, K, act); break;
+        case 2: gemv_kernel<2><<<grid, 256, 0, s>>>(x, W, bias, residual, y, N, K, act); break;
+        case 3: gemv_kernel<3><<<grid, 256, 0, s>>>(x, W, bias, residual, y, N, K, act); break;
+        default: gemv_kernel<4><<<grid, 256, 0, s>>>(x, W, bias, residual, y, N, K, act); break;
+    }
+    return check_launch("gemv");
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

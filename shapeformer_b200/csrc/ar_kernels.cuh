@@ -29,8 +29,12 @@ int launch_add_target(const float *x_in, float *x_out, const int64_t *tokens, co
                       int t0, int T, const int32_t *st, cudaStream_t s, int Tin);
 int launch_take_last(const float *x, float *out, int B, int d, int T, cudaStream_t s);
 int launch_layernorm(const float *x, const float *w, const float *b, float *y, int rows, int d, cudaStream_t s);
+int launch_gemv(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
+                int act, cudaStream_t s);
 int launch_linear(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
                   int act, cudaStream_t stream);
+int launch_linear_tc(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
+                     int act, cudaStream_t stream);
 int launch_attn_decode(const float *qkv, float *kc, float *vc, float *out, float *part, int B, int H, int max_len, int pos,
                        const int32_t *st, int n_split, cudaStream_t s);
 int launch_attn_prefill(const float *qkv, float *kc, float *vc, float *out, int B, int H, int T, int max_len,

@@ -65,6 +65,11 @@ int sfb200_linear(const float *x, const float *W, const float *bias, const float
     if (!x || !W || !y || (act != 0 && act != 1)) return SFB200_E_ARG;
     return launch_linear(x, W, bias, residual, y, M, N, K, act, as_stream(stream));
 }
+int sfb200_linear_tc(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
+                     int act, void *stream) {
+    if (!x || !W || !y || (act != 0 && act != 1)) return SFB200_E_ARG;
+    return launch_linear_tc(x, W, bias, residual, y, M, N, K, act, as_stream(stream));
+}
 int sfb200_layernorm(const float *x, const float *w, const float *b, float *y, int rows, int d, void *stream) {
     if (!x || !w || !b || !y) return SFB200_E_ARG;
     return launch_layernorm(x, w, b, y, rows, d, as_stream(stream));

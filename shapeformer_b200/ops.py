@@ -18,6 +18,17 @@ def linear(x, W, bias=None, residual=None, act=None):
     return y
 
 
+def linear_tc(x, W, bias=None, residual=None, act=None):
+    """linear() on the tcgen05 tensor cores (3xTF32 with periodic fp32 promotion: fp32-level accuracy)."""
+    lib = _lib.load()
+    M, K = x.shape
+    N = W.shape[0]
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    _lib.check(lib.sfb200_linear_tc(_lib.ptr(x), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(residual), _lib.ptr(y), M, N, K,
+                                    1 if act == "gelu" else 0, _lib.stream_ptr()), "sfb200_linear_tc")
+    return y
+
+
 def layernorm(x, w, b):
     lib = _lib.load()
     rows, d = x.shape

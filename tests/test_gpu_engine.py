@@ -143,3 +143,27 @@ def test_full_64cubed_decode_properties(cuda):
     sel = torch.randperm(64 ** 3, generator=torch.Generator().manual_seed(1))[:4096]
     ref = O.decode_index(sd, code[:1], Xtg[:, sel])["logits"]
     assert (full[0, sel.to(cuda)].cpu() - ref[0]).abs().max() < 1e-4
+
+
+def test_sampler_shipped_model_matches_oracle(cuda):
+    """The SHIPPED transformer size (20+4 layers, d=1024, 16 heads, 325M parameters): tokens identical to the oracle and
+    logits history within 5e-5 — exercises the tcgen05 3xTF32 GEMMs at K = 1024 / 4096 and cluster split-K."""
+    cfg = synth.SHIPPED_GPT
+    sd = synth.gpt_state_dict(cfg, seed=314, peaky=True)
+    B, Lc, steps = 12, 24, 6
+    c = synth.cond_indices(B, Lc, seed=7)
+    noise = util.noise_from_seed(9, steps, B, 4097)
+    ox, oh = O.sample_indices(sd, O.GPTSpec(**cfg), c, c[:, :0], steps, END, True, 50, 0.9, 1.0, True, True,
+                              noise=O.ListNoise(noise.reshape(-1, B, 4097)), cached=True)
+    s = make_sampler(cuda, cfg, sd, B, Lc, steps)
+    x, hist = s.sample(c, steps, top_k=50, top_p=0.9, best_in_first=True, mask_invalid=True, mask_invalid_completion=True,
+                       noise=noise, use_graph=True)
+    worst = 0.0
+    for a, b in zip(hist, oh):
+        a = a.cpu()
+        fin = torch.isfinite(b)
+        assert torch.equal(torch.isfinite(a), fin)
+        worst = max(worst, (a[fin] - b[fin]).abs().max().item())
+    print("shipped-size max |dlogit| =", worst)
+    assert torch.equal(x.cpu(), ox)
+    assert worst < 5e-5, worst

@@ -139,3 +139,33 @@ def test_ar_sample_small_vocab(cuda):
     tk = tokens.to(cuda)
     ops.ar_sample(logits.to(cuda), tk, 1, 1, 0, qs.to(cuda), qb.to(cuda), (36, 36), 5, 0.9, 1.0, False, True, False)
     assert torch.equal(tk[:, 1, 0].cpu(), new)
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 128, 64), (64, 1024, 1024), (16, 3072, 1024), (17, 4097, 1024), (33, 1024, 4096),
+                                   (64, 4096, 1024), (64, 4097, 1024), (1, 256, 128), (200, 384, 128), (1000, 1024, 1024),
+                                   (4096, 1024, 1024)])
+@pytest.mark.parametrize("mode", ["plain", "bias_gelu", "bias_res"])
+def test_linear_tc(cuda, M, N, K, mode):
+    """tcgen05 3xTF32 GEMM: fp32-level accuracy (not TF32-level) against an fp64 reference."""
+    x, W, b, r = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05), rnd(N, seed=3), rnd(M, N, seed=4)
+    xd, Wd = x.double(), W.double()
+    if mode == "plain":
+        ref = xd @ Wd.t()
+        out = ops.linear_tc(x.to(cuda), W.to(cuda))
+    elif mode == "bias_gelu":
+        ref = F.gelu(xd @ Wd.t() + b.double())
+        out = ops.linear_tc(x.to(cuda), W.to(cuda), b.to(cuda), act="gelu")
+    else:
+        ref = r.double() + xd @ Wd.t() + b.double()
+        out = ops.linear_tc(x.to(cuda), W.to(cuda), b.to(cuda), residual=r.to(cuda))
+    err = (out.cpu().double() - ref).abs().max().item()
+    scale = max(1.0, ref.abs().max().item())
+    assert err < 2.5e-6 * scale * max(1.0, (K / 1024) ** 0.5), (err, scale)   # single-pass TF32 would be ~1e-3
+
+
+def test_linear_tc_deterministic_and_in_place(cuda):
+    x, W, b = rnd(64, 1024, seed=1).to(cuda), rnd(1024, 1024, seed=2, scale=0.03).to(cuda), rnd(1024, seed=3).to(cuda)
+    r = rnd(64, 1024, seed=4).to(cuda)
+    a = ops.linear_tc(x, W, b, residual=r)
+    for _ in range(5):
+        assert torch.equal(a, ops.linear_tc(x, W, b, residual=r))   # split-K partials are summed in split order
