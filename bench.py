@@ -105,6 +105,27 @@ def ncu_traffic(alg_bytes_per_launch):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+def pick_cpu_threads(gpt_sd, cfg):
+    """torch's CPU kernels do not scale to every core of a big host (128 threads were 20x slower than 8 on the bench box):
+    time one transformer block of the reference algorithm at L = 256 for several thread counts and keep the fastest."""
+    from oracle import sf_oracle as O
+    n = os.cpu_count() or 1
+    x = torch.randn(1, 256, cfg["n_embd"])
+    best, best_t = 1, float("inf")
+    for t in sorted({c for c in (4, 8, 16, 32, 64, n) if c <= n}):
+        torch.set_num_threads(t)
+        with torch.no_grad():
+            O.gpt_block(gpt_sd, "blocks.0.0.", x, cfg["n_head"])
+            t0 = time.perf_counter()
+            for _ in range(3):
+                O.gpt_block(gpt_sd, "blocks.0.0.", x, cfg["n_head"])
+            dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = t, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_reference_sample(args, gpt_sd, vq_sd, cfg, threads):
     """The reference algorithm on the host cores (oracle port, faithful = UNCACHED like the reference): time one row's AR
     step at three context lengths and one 64^3 decode, then integrate over the 512-step schedule.  Returns a dict."""
@@ -149,7 +170,7 @@ def cpu_reference_sample(args, gpt_sd, vq_sd, cfg, threads):
         O.decode_index(vq_sd, code, Xtg)
     dec = time.perf_counter() - t0
     per_row = ar + dec
-    return {"value": 1.0 / per_row, "unit": "shapes/s", "cores": threads, "kind": "port",
+    return {"value": 1.0 / per_row, "unit": "shapes/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
             "sample": (f"oracle port of the reference (uncached full forward per step, torch CPU fp32), 1 row: AR steps timed "
                        f"at L={lens} ({', '.join(f'{t_at[l]:.2f}s' for l in lens)}) integrated over {S} steps = {ar:.0f}s, "
                        f"+ one {args.grid}^3 decode = {dec:.2f}s; cost is linear in rows"),
@@ -177,9 +198,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        threads = os.cpu_count() or 1
         gpt_sd = synth.gpt_state_dict(cfg, seed=314, peaky=False)
         vq_sd = synth.vqdif_state_dict(seed=314)
+        threads = pick_cpu_threads(gpt_sd, cfg)
         vals, secs = [], []
         for i in range(args.warmup + args.steps):
             r = cpu_reference_sample(args, gpt_sd, vq_sd, cfg, threads)
@@ -351,7 +372,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sd_cpu = {k: v.detach().cpu() for k, v in model.transformer.state_dict().items()}
         vq_cpu = {k: v.detach().cpu() for k, v in vq.state_dict().items()}
-        cpu = cpu_reference_sample(args, sd_cpu, vq_cpu, cfg, os.cpu_count() or 1)
+        cpu = cpu_reference_sample(args, sd_cpu, vq_cpu, cfg, pick_cpu_threads(sd_cpu, cfg))
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": "shapes/s", "n_gpus": world, "steps": args.steps,

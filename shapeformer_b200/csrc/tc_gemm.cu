@@ -32,7 +32,8 @@ using namespace tc;
 
 constexpr int TCG_NT = 4;   // TMEM A slots == x hi/lo slots (split warps may run this many chunks ahead of the MMAs)
 constexpr int TCG_G = 2;    // chunks per promotion group (24 MMAs per TMEM accumulation chain)
-constexpr int TCG_THREADS = 160;
+constexpr int TCG_THREADS = 288;   // 8 load/split/promote warps (two per W row: K halves) + 1 MMA warp
+constexpr int TCG_SPLIT = 256;     // threads in the split warps
 
 template <int BN>
 struct TcgSmem {
@@ -65,6 +66,7 @@ tc_linear_kernel(const float *__restrict__ x, const float *__restrict__ W, const
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(dfree + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & 127, half = (tid >> 7) & 1;   // split warps: W row / TMEM lane, and which half of K (and of D columns)
     const int n0 = blockIdx.x * 128, m0 = blockIdx.z * BN, sp = blockIdx.y;
     const int nch_total = K / 32;
     const int c_beg = (int)(((long long)sp * nch_total) / splits), c_end = (int)(((long long)(sp + 1) * nch_total) / splits);
@@ -75,49 +77,50 @@ tc_linear_kernel(const float *__restrict__ x, const float *__restrict__ W, const
     constexpr uint32_t IDESC = instr_desc(2, 128, BN);
 
     if (tid == 0) {
-        for (int i = 0; i < TCG_NT; ++i) { mbar_init(&full[i], 128); mbar_init(&done[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&dfull[i], 1); mbar_init(&dfree[i], 128); }
+        for (int i = 0; i < TCG_NT; ++i) { mbar_init(&full[i], TCG_SPLIT); mbar_init(&done[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&dfull[i], 1); mbar_init(&dfree[i], TCG_SPLIT); }
         mbar_fence_init();
     }
-    if (warp == 4) tmem_alloc<TM_COLS>(tmem_slot);
+    if (warp == 8) tmem_alloc<TM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    float acc[BN];   // meaningful in warps 0-3 only: acc[j] = D[row tid][col j]
+    constexpr int HB = BN / 2;   // D columns owned by one thread of a row pair
+    float acc[HB];               // split warps: acc[j] = D[row][half * HB + j]
 #pragma unroll
-    for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+    for (int j = 0; j < HB; ++j) acc[j] = 0.f;
 
-    if (warp < 4) {
+    if (warp < 8) {
         // ================================ load + split + promote warps ================================
         auto issue_loads = [&](int c, int s) {
             const int k0 = (c_beg + c) * 32;
             float *wdst = reinterpret_cast<float *>(smem + L::OFF_W + s * L::W_TILE);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int idx = tid + 128 * j, row = idx >> 3, ch = idx & 7, n = n0 + row;
+            for (int j = 0; j < 4; ++j) {
+                const int idx = tid + TCG_SPLIT * j, r = idx >> 3, ch = idx & 7, n = n0 + r;
                 const float *src = W + (size_t)(n < N ? n : N - 1) * K + k0 + ch * 4;
-                cp_async16(wdst + row * 32 + ((ch ^ (row & 7)) << 2), src, n < N ? 16 : 0);
+                cp_async16(wdst + r * 32 + ((ch ^ (r & 7)) << 2), src, n < N ? 16 : 0);
             }
             float *xdst = reinterpret_cast<float *>(smem + L::OFF_X + s * L::X_TILE);
 #pragma unroll
-            for (int j = 0; j < BN / 16; ++j) {
-                const int idx = tid + 128 * j, row = idx >> 3, ch = idx & 7, m = m0 + row;
+            for (int j = 0; j < BN / 32; ++j) {
+                const int idx = tid + TCG_SPLIT * j, r = idx >> 3, ch = idx & 7, m = m0 + r;
                 const float *src = x + (size_t)(m < M ? m : M - 1) * K + k0 + ch * 4;
-                cp_async16(xdst + row * 32 + ((ch ^ (row & 7)) << 2), src, m < M ? 16 : 0);
+                cp_async16(xdst + r * 32 + ((ch ^ (r & 7)) << 2), src, m < M ? 16 : 0);
             }
         };
-        const uint32_t lane_off = (uint32_t)(32 * warp) << 16;
+        const uint32_t lane_off = (uint32_t)(32 * (warp & 3)) << 16;
         // drain promotion group g: acc += D[g & 1]
         auto drain = [&](int g) {
             const int b = g & 1;
             mbar_wait(&dfull[b], (g >> 1) & 1);
             tc_fence_after();
 #pragma unroll
-            for (int h = 0; h < BN / 32; ++h) {
+            for (int h = 0; h < HB / 32; ++h) {
                 uint32_t v[32];
-                tmem_ld32(tmem_base + lane_off + b * BN + h * 32, v);
+                tmem_ld32(tmem_base + lane_off + b * BN + half * HB + h * 32, v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc[h * 32 + j] += __uint_as_float(v[j]);
@@ -132,35 +135,36 @@ tc_linear_kernel(const float *__restrict__ x, const float *__restrict__ W, const
         }
         for (int i = 0; i < nch; ++i) {
             cp_async_wait<TCG_NS - 2>();     // this thread's copies of chunk i have landed
-            bar_sync(1, 128);                // ... everybody's; and everybody finished splitting chunk i-1
+            bar_sync(1, TCG_SPLIT);          // ... everybody's; and everybody finished splitting chunk i-1
             if (i + TCG_NS - 1 < nch) issue_loads(i + TCG_NS - 1, (i + TCG_NS - 1) % TCG_NS);
             cp_async_commit();
             const int slot = i % TCG_NT;
             if (i >= TCG_NT) mbar_wait(&done[slot], ((i / TCG_NT) - 1) & 1);   // MMAs of chunk i-NT released the slot
             tc_fence_after();
-            // ---- W row `tid` -> hi | lo in tensor memory
-            const float *wrow = reinterpret_cast<const float *>(smem + L::OFF_W + (i % TCG_NS) * L::W_TILE) + tid * 32;
+            // ---- half of W row `row` (16 of its 32 k) -> hi | lo in tensor memory
+            const float *wrow = reinterpret_cast<const float *>(smem + L::OFF_W + (i % TCG_NS) * L::W_TILE) + row * 32;
             {
-                uint32_t hi[32], lo[32];
+                uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    const float4 v = ld4(wrow + ((ch ^ (tid & 7)) << 2));
-                    split_tf32(v.x, hi[4 * ch + 0], lo[4 * ch + 0]);
-                    split_tf32(v.y, hi[4 * ch + 1], lo[4 * ch + 1]);
-                    split_tf32(v.z, hi[4 * ch + 2], lo[4 * ch + 2]);
-                    split_tf32(v.w, hi[4 * ch + 3], lo[4 * ch + 3]);
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const int ch = half * 4 + c4;
+                    const float4 v = ld4(wrow + ((ch ^ (row & 7)) << 2));
+                    split_tf32(v.x, hi[4 * c4 + 0], lo[4 * c4 + 0]);
+                    split_tf32(v.y, hi[4 * c4 + 1], lo[4 * c4 + 1]);
+                    split_tf32(v.z, hi[4 * c4 + 2], lo[4 * c4 + 2]);
+                    split_tf32(v.w, hi[4 * c4 + 3], lo[4 * c4 + 3]);
                 }
-                const uint32_t a_col = tmem_base + lane_off + A_COL0 + slot * 64;
-                tmem_st32(a_col, hi);
-                tmem_st32(a_col + 32, lo);
+                const uint32_t a_col = tmem_base + lane_off + A_COL0 + slot * 64 + half * 16;
+                tmem_st16(a_col, hi);
+                tmem_st16(a_col + 32, lo);
             }
             // ---- x tile -> hi / lo shared tiles (same swizzled positions)
             const float *xr = reinterpret_cast<const float *>(smem + L::OFF_X + (i % TCG_NS) * L::X_TILE);
             float *xh = reinterpret_cast<float *>(smem + L::OFF_XH + slot * L::X_TILE);
             float *xl = reinterpret_cast<float *>(smem + L::OFF_XL + slot * L::X_TILE);
 #pragma unroll
-            for (int j = 0; j < BN / 16; ++j) {
-                const int o = (tid + 128 * j) * 4;
+            for (int j = 0; j < BN / 32; ++j) {
+                const int o = (tid + TCG_SPLIT * j) * 4;
                 const float4 v = ld4(xr + o);
                 uint32_t h[4], l[4];
                 split_tf32(v.x, h[0], l[0]); split_tf32(v.y, h[1], l[1]);
@@ -182,7 +186,7 @@ tc_linear_kernel(const float *__restrict__ x, const float *__restrict__ W, const
         drain(ngroups - 1);
     } else {
         // ================================ MMA issuer (one elected thread of warp 4) ================================
-        if ((tid & 31) == 0) {
+        if ((tid & 31) == 0) {   // warp 8
             const uint32_t xh0 = smem_u32(smem + L::OFF_XH), xl0 = smem_u32(smem + L::OFF_XL);
             for (int i = 0; i < nch; ++i) {
                 const int slot = i % TCG_NT, g = i / TCG_G, b = g & 1;
@@ -210,19 +214,19 @@ tc_linear_kernel(const float *__restrict__ x, const float *__restrict__ W, const
     }
     tc_fence_before();
     __syncthreads();      // operand ring is idle from here on; TMEM is no longer needed
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after();
         tmem_dealloc<TM_COLS>(tmem_base);
     }
 
     // ================================ epilogue ================================
-    const int n = n0 + tid;
+    const int n = n0 + row;
     if (splits == 1) {
-        if (warp < 4) {
+        if (warp < 8) {
             const float bv = (bias && n < N) ? bias[n] : 0.f;
 #pragma unroll
-            for (int j = 0; j < BN; ++j) {
-                const int m = m0 + j;
+            for (int j = 0; j < HB; ++j) {
+                const int m = m0 + half * HB + j;
                 if (m < M && n < N) {
                     float r = acc[j] + bv;
                     if (act == 1) r = gelu_erf_tc(r);
@@ -234,9 +238,9 @@ tc_linear_kernel(const float *__restrict__ x, const float *__restrict__ W, const
     } else {
         cg::cluster_group cluster = cg::this_cluster();
         float *red = reinterpret_cast<float *>(smem);   // [BN][128] partial tile, reusing the operand ring
-        if (warp < 4) {
+        if (warp < 8) {
 #pragma unroll
-            for (int j = 0; j < BN; ++j) red[j * 128 + tid] = acc[j];
+            for (int j = 0; j < HB; ++j) red[(half * HB + j) * 128 + row] = acc[j];
         }
         cluster.sync();
         const int rank = (int)cluster.block_rank();

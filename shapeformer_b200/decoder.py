@@ -63,11 +63,11 @@ def conv_prologue(sd, x, prefix="decoder."):
 
 
 class ImplicitDecoder:
-    """decode_index for batches of code grids.  `sd`: VQDIF state dict (decoder.*, quantizer.embedding.weight) on the
-    target CUDA device."""
+    """decode_index for batches of code grids.  `sd`: VQDIF state dict (decoder.*, quantizer.embedding.weight).
+    impl: 0 = tcgen05 tensor-core point kernel (default), 1 = fp32 FFMA point kernel (kept for cross-checking)."""
     _active = None   # which instance's MLP weights currently sit in the library's constant bank
 
-    def __init__(self, sd, device, impl=1, prefix="decoder.", codebook_key="quantizer.embedding.weight"):
+    def __init__(self, sd, device, impl=0, prefix="decoder.", codebook_key="quantizer.embedding.weight"):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":

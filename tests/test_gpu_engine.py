@@ -75,13 +75,14 @@ def test_sampler_device_rng_is_the_multinomial_stream(cuda):
     assert torch.equal(x1, x2)
 
 
-def test_decoder_golden_and_oracle(cuda):
+@pytest.mark.parametrize("impl", [0, 1])
+def test_decoder_golden_and_oracle(cuda, impl):
     g = torch.load(util.GOLDEN + "/decoder.pt")
     sd = synth.vqdif_state_dict(seed=g["wseed"])
     code = synth.code_grids(1, seed=g["code_seed"])
     gen = torch.Generator().manual_seed(g["pts_seed"])
     Xtg = torch.rand(1, g["n"], 3, generator=gen) * 2 - 1
-    dec = decoder.ImplicitDecoder(sd, cuda, impl=1)
+    dec = decoder.ImplicitDecoder(sd, cuda, impl=impl)
     out = dec.decode_index(code, Xtg)["logits"]
     assert out.shape == (1, g["n"], 1)
     err = (out[0, :, 0].cpu() - g["logits"]).abs().max().item()
@@ -90,9 +91,10 @@ def test_decoder_golden_and_oracle(cuda):
     assert (occ - torch.sigmoid(g["logits"])).abs().max() < 1e-4
 
 
-def test_decoder_pieces_vs_oracle(cuda):
+@pytest.mark.parametrize("impl", [0, 1])
+def test_decoder_pieces_vs_oracle(cuda, impl):
     sd = synth.vqdif_state_dict(seed=6)
-    dec = decoder.ImplicitDecoder(sd, cuda, impl=1)
+    dec = decoder.ImplicitDecoder(sd, cuda, impl=impl)
     code = synth.code_grids(2, seed=1)
     # get_code: exact
     assert torch.equal(dec.get_code(code).cpu(), O.get_code(sd, code))
@@ -129,15 +131,21 @@ def test_tokens_to_dense(cuda):
         assert torch.equal(out[b], O.tokens_to_dense(toks[b], empty[b]))
 
 
-def test_full_64cubed_decode_properties(cuda):
+@pytest.mark.parametrize("impl", [0, 1])
+def test_full_64cubed_decode_properties(cuda, impl):
     """BASELINE size (262,144 query points): size-independent checks — a shape decoded alone equals the same shape inside a
     batch, and a random 4,096-point subset matches the oracle."""
     sd = synth.vqdif_state_dict(seed=6)
-    dec = decoder.ImplicitDecoder(sd, cuda, impl=1)
+    dec = decoder.ImplicitDecoder(sd, cuda, impl=impl)
     code = synth.code_grids(2, seed=5)
     Xtg = synth.make_grid(64)[None]
     full = dec.decode_index(code, Xtg)["logits"]
     assert full.shape == (2, 64 ** 3, 1)
+    if impl == 0:   # the two point kernels agree with each other on the full grid (same feature grid, same points)
+        other = dec.decode_points(dec.feature_grid(dec.get_code(code)), Xtg, impl=1)
+        assert (full[..., 0] - other).abs().max() < 2e-5
+        occ = dec.occupancy(code, Xtg)
+        assert (occ - torch.sigmoid(full[..., 0])).abs().max() < 1e-6
     alone = dec.decode_index(code[1:], Xtg)["logits"]
     assert (full[1] - alone[0]).abs().max() < 1e-5     # cuDNN may pick another algorithm for B=1; MLP kernel is bitwise
     sel = torch.randperm(64 ** 3, generator=torch.Generator().manual_seed(1))[:4096]
