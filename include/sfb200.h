@@ -153,6 +153,12 @@ typedef struct sfb200_ar_sampling {
  * CondTupleGPT.sample_next_tuple (transformer/mingpt.py:297-310) and AR_N.get_extra_indices (representers.py:187-196). */
 int sfb200_ar_begin(sfb200_ar *h, int B, int L_cond, const sfb200_ar_sampling *sp, void *stream);
 
+/* Same, with conditioning sharing: row_src (HOST array of B ints, row_src[b] <= b) names an earlier row whose conditioning
+ * tuples are identical to row b's (row_src[b] == b for the first row of each group) — the reference's sample_n expansion of one
+ * shape (shapeformer/shapeformer.py:229).  Only the group leaders are pushed through the prefill; the other rows receive a
+ * copy of the leader's prefix K/V.  Results are identical to sfb200_ar_begin. */
+int sfb200_ar_begin_shared(sfb200_ar *h, int B, int L_cond, const sfb200_ar_sampling *sp, const int32_t *row_src, void *stream);
+
 /* Run `n_steps` AR steps (each = pos sub-pass + val sub-pass = one (pos,val) tuple per row), enqueued back to back.
  * noise: (n_steps, 4, B, Vmax) fp32 Exp(1) draws in the reference's order per step: pos-sample, pos-best, val-sample,
  * val-best (what torch.multinomial draws internally, shapeformer/common.py:296; Vmax = max(vocab)).

@@ -58,6 +58,7 @@ SIGNATURES = {
     "sfb200_ar_create": (ctypes.c_int, [ctypes.POINTER(ArConfig), vp, vp, vp, vp, vp, ctypes.POINTER(vp)]),
     "sfb200_ar_destroy": (None, [vp]),
     "sfb200_ar_begin": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ArSampling), vp]),
+    "sfb200_ar_begin_shared": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ArSampling), vp, vp]),
     "sfb200_ar_steps": (ctypes.c_int, [vp, ctypes.c_int, vp, ctypes.c_int, vp]),
     "sfb200_ar_status_ptr": (vp, [vp]),
     "sfb200_ar_profile": (ctypes.c_int, [vp, ctypes.c_int]),

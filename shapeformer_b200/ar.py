@@ -145,7 +145,7 @@ class ARSampler:
 
     def sample(self, c_indices, max_steps, top_k=100, top_p=0.8, temperature=1.0, best_in_first=False,
                mask_invalid=True, mask_invalid_completion=False, noise=None, generator=None, use_graph=True,
-               stop_early=True):
+               stop_early=True, share_prefix=True):
         """Run the AR loop.  c_indices (B, L_c, 2) int64 (any device).  noise: optional (>= max_steps, 4, B, Vmax)
         tensor of Exp(1) draws to use instead of the device RNG (parity tests).  Returns (x (B, steps, 2) int64 on the
         device, [hist0, hist1] device views (B, steps, V) or None)."""
@@ -163,7 +163,17 @@ class ARSampler:
         sp = _lib.ArSampling(int(top_k), float(top_p), float(temperature), int(bool(best_in_first)),
                              int(bool(mask_invalid)), int(bool(mask_invalid_completion)))
         stream = _lib.stream_ptr()
-        _lib.check(self.lib.sfb200_ar_begin(self.handle, B, L_c, ctypes.byref(sp), stream), "sfb200_ar_begin")
+        # rows with identical conditioning (the reference's sample_n expansion) share one prefill
+        row_src, seen = (ctypes.c_int32 * B)(), {}
+        if share_prefix:
+            c_host = c_indices.detach().cpu().contiguous()
+            for b in range(B):
+                row_src[b] = seen.setdefault(c_host[b].numpy().tobytes(), b)
+        else:
+            for b in range(B):
+                row_src[b] = b
+        _lib.check(self.lib.sfb200_ar_begin_shared(self.handle, B, L_c, ctypes.byref(sp),
+                                                   ctypes.cast(row_src, ctypes.c_void_p), stream), "sfb200_ar_begin_shared")
         done, steps = 0, max_steps
         while done < max_steps:
             n = min(self.chunk_steps, max_steps - done)

@@ -73,7 +73,7 @@ static int64_t weight_offset(const Layout *L, int id, int g, int l) {
 }
 
 struct Buffers {   // byte offsets into the workspace
-    int64_t st, x0, x1, h, qkv, att, ff, logits[2], part;
+    int64_t st, rowmap, x0, x1, h, qkv, att, ff, logits[2], part;
     int64_t px, px1, ph, pqkv, pff;
     int64_t total;
 };
@@ -92,6 +92,7 @@ static void carve(const sfb200_ar_config *c, Buffers *b) {
     int64_t o = 0;
     auto take = [&](int64_t bytes) { int64_t r = o; o = align_up(o + bytes, 256); return r; };
     b->st = take(ST_WORDS * 4);
+    b->rowmap = take(3 * B * 4);    // prefill leaders | duplicate rows | their sources
     b->x0 = take(B * d * F);
     b->x1 = take(B * d * F);
     b->h = take(B * d * F);
@@ -236,12 +237,15 @@ static int linear(sfb200_ar *h, const float *x, const float *W, const float *bia
 }
 
 // One transformer block over M = rows*T positions (prefill) — Block.forward, transformer/mingpt.py:108-111.
-static int block_prefill(sfb200_ar *h, int g, int l, float *x, int row0, int rows, int T, cudaStream_t s) {
+static int block_prefill(sfb200_ar *h, int g, int l, float *x, int row0, int rows, int T, cudaStream_t s,
+                         const int32_t *rowmap) {
     const int d = h->cfg.n_embd, H = h->cfg.n_head, M = rows * T;
     float *ph = WS_<float>(h, h->buf.ph), *pqkv = WS_<float>(h, h->buf.pqkv), *pff = WS_<float>(h, h->buf.pff);
     SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN1_W, g, l), W_(h, SFB200_W_LN1_B, g, l), ph, M, d, s));
     SFB_TRY(linear(h, ph, W_(h, SFB200_W_QKV_W, g, l), W_(h, SFB200_W_QKV_B, g, l), nullptr, pqkv, M, 3 * d, d, 0, s));
-    SFB_TRY(launch_attn_prefill(pqkv, kcache(h, g, l, row0), vcache(h, g, l, row0), ph, rows, H, T, h->cfg.max_len, s));
+    // with a rowmap the cache rows are rowmap[i] (cache base = row 0), otherwise rows row0 .. row0+rows-1
+    SFB_TRY(launch_attn_prefill(pqkv, kcache(h, g, l, rowmap ? 0 : row0), vcache(h, g, l, rowmap ? 0 : row0), ph, rows, H, T,
+                                h->cfg.max_len, s, rowmap));
     SFB_TRY(linear(h, ph, W_(h, SFB200_W_PROJ_W, g, l), W_(h, SFB200_W_PROJ_B, g, l), x, x, M, d, d, 0, s));
     SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN2_W, g, l), W_(h, SFB200_W_LN2_B, g, l), ph, M, d, s));
     SFB_TRY(linear(h, ph, W_(h, SFB200_W_FC1_W, g, l), W_(h, SFB200_W_FC1_B, g, l), nullptr, pff, M, 4 * d, d, 1, s));
@@ -292,7 +296,8 @@ static int head(sfb200_ar *h, int g, const float *x, float *logits, int rows, cu
     return SFB200_OK;
 }
 
-extern "C" int sfb200_ar_begin(sfb200_ar *h, int B, int L_cond, const sfb200_ar_sampling *sp, void *stream) {
+extern "C" int sfb200_ar_begin_shared(sfb200_ar *h, int B, int L_cond, const sfb200_ar_sampling *sp, const int32_t *row_src,
+                                      void *stream) {
     if (!h || !sp) return SFB200_E_ARG;
     if (B < 1 || B > h->cfg.max_rows || L_cond < 1 || L_cond > h->cfg.max_cond) return SFB200_E_ARG;
     if (!(sp->temperature > 0.f)) return SFB200_E_ARG;
@@ -303,28 +308,56 @@ extern "C" int sfb200_ar_begin(sfb200_ar *h, int B, int L_cond, const sfb200_ar_
     h->steps_host = 0;
     int32_t *st = WS_<int32_t>(h, h->buf.st);
     SFB_TRY(launch_state_init(st, L_cond, s));
+    // ---- group leaders / duplicates
+    std::vector<int32_t> lead, dup_dst, dup_src;
+    for (int b = 0; b < B; ++b) {
+        const int src = row_src ? row_src[b] : b;
+        if (src < 0 || src > b || (row_src && row_src[src] != src)) return SFB200_E_ARG;
+        if (src == b) lead.push_back(b); else { dup_dst.push_back(b); dup_src.push_back(src); }
+    }
+    const int n_lead = (int)lead.size(), n_dup = (int)dup_dst.size();
+    int32_t *rm = WS_<int32_t>(h, h->buf.rowmap);
+    const int32_t *rm_lead = nullptr, *rm_dst = rm + h->cfg.max_rows, *rm_src = rm + 2 * h->cfg.max_rows;
+    if (n_dup > 0) {
+        SFB_CUDA_TRY(cudaMemcpyAsync(rm, lead.data(), n_lead * 4, cudaMemcpyHostToDevice, s));
+        SFB_CUDA_TRY(cudaMemcpyAsync(rm + h->cfg.max_rows, dup_dst.data(), n_dup * 4, cudaMemcpyHostToDevice, s));
+        SFB_CUDA_TRY(cudaMemcpyAsync(rm + 2 * h->cfg.max_rows, dup_src.data(), n_dup * 4, cudaMemcpyHostToDevice, s));
+        SFB_CUDA_TRY(cudaStreamSynchronize(s));   // the host vectors go out of scope (pageable staging); B ints, once per batch
+        rm_lead = rm;
+    }
     float *px = WS_<float>(h, h->buf.px), *px1 = WS_<float>(h, h->buf.px1), *x0 = WS_<float>(h, h->buf.x0);
     const int64_t end0 = h->cfg.end_tokens[0];
-    for (int r0 = 0; r0 < B; r0 += h->cfg.prefill_rows) {
-        const int rows = (B - r0 < h->cfg.prefill_rows) ? B - r0 : h->cfg.prefill_rows;
-        const int64_t *tok = h->tokens + (int64_t)r0 * h->cfg.max_len * 2;
+    for (int r0 = 0; r0 < n_lead; r0 += h->cfg.prefill_rows) {
+        const int rows = (n_lead - r0 < h->cfg.prefill_rows) ? n_lead - r0 : h->cfg.prefill_rows;
+        // without sharing the chunk is rows r0.. of every buffer; with sharing a row list selects tokens / cache / x0 rows
+        const int32_t *map = rm_lead ? rm_lead + r0 : nullptr;
+        const int64_t *tok = h->tokens + (map ? 0 : (int64_t)r0 * h->cfg.max_len * 2);
         SFB_TRY(launch_embed(tok, W_(h, SFB200_W_TOK_EMB0, 0, 0), W_(h, SFB200_W_TOK_EMB1, 0, 0),
                              W_(h, SFB200_W_EXTRA_EMB, 0, 0), W_(h, SFB200_W_POS_EMB, 0, 0),
                              W_(h, SFB200_W_COND_POS_EMB, 0, 0), px, rows, d, h->cfg.max_len, 0, L_cond, L_cond, end0,
-                             nullptr, s));
-        for (int l = 0; l < h->cfg.n_layers[0]; ++l) SFB_TRY(block_prefill(h, 0, l, px, r0, rows, L_cond, s));
-        SFB_TRY(launch_take_last(px, x0 + (int64_t)r0 * d, rows, d, L_cond, s));
+                             nullptr, s, map));
+        for (int l = 0; l < h->cfg.n_layers[0]; ++l) SFB_TRY(block_prefill(h, 0, l, px, r0, rows, L_cond, s, map));
+        SFB_TRY(launch_take_last(px, map ? x0 : x0 + (int64_t)r0 * d, rows, d, L_cond, s, map));
         const int T1 = L_cond - 1;
         if (T1 > 0) {
             // blocks[1] input of position t is blocks[0] output + tok_embs[0](pos of tuple t+1)   (mingpt.py:309)
             SFB_TRY(launch_add_target(px, px1, tok, W_(h, SFB200_W_TOK_EMB0, 0, 0), rows, d, h->cfg.max_len, 0, T1, nullptr,
-                                      s, L_cond));
-            for (int l = 0; l < h->cfg.n_layers[1]; ++l) SFB_TRY(block_prefill(h, 1, l, px1, r0, rows, T1, s));
+                                      s, L_cond, map));
+            for (int l = 0; l < h->cfg.n_layers[1]; ++l) SFB_TRY(block_prefill(h, 1, l, px1, r0, rows, T1, s, map));
         }
+    }
+    if (n_dup > 0) {
+        const int64_t per = (int64_t)h->cfg.max_rows * h->cfg.n_head * h->cfg.max_len * 64;
+        SFB_TRY(launch_prefix_copy(h->kv, x0, rm_dst, rm_src, n_dup, h->cfg.n_head, h->cfg.max_len, L_cond, d,
+                                   h->cfg.n_layers[0] + h->cfg.n_layers[1], per, s));
     }
     SFB_TRY(head(h, 0, x0, WS_<float>(h, h->buf.logits[0]), B, s));
     h->begun = true;
     return SFB200_OK;
+}
+
+extern "C" int sfb200_ar_begin(sfb200_ar *h, int B, int L_cond, const sfb200_ar_sampling *sp, void *stream) {
+    return sfb200_ar_begin_shared(h, B, L_cond, sp, nullptr, stream);
 }
 
 // One AR step: sample pos -> blocks[1] + head[1] for position L-1 -> sample val -> L += 1 -> blocks[0] + head[0] for the

@@ -21,6 +21,8 @@ namespace sfb {
 //   st[ST_CHUNK]  step index inside the current sfb200_ar_steps call (selects the noise slab)
 
 __global__ void ar_state_init_kernel(int32_t *st, int L_cond) {
+    pdl_trigger();
+    pdl_wait();
     if (threadIdx.x == 0) {
         st[ST_STEPS] = 0;
         st[ST_ENDED] = -1;
@@ -30,11 +32,15 @@ __global__ void ar_state_init_kernel(int32_t *st, int L_cond) {
     }
 }
 __global__ void ar_chunk_reset_kernel(int32_t *st) {
+    pdl_trigger();
+    pdl_wait();
     if (threadIdx.x == 0) st[ST_CHUNK] = 0;
 }
 
 // After the val sub-pass: end detection (shapeformer.py:110-115) and L += 1.
 __global__ void ar_advance_kernel(int32_t *st, const int64_t *tokens, int B, int max_len, int64_t end0, int64_t end1) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ int not_ended;
     if (threadIdx.x == 0) not_ended = 0;
     __syncthreads();
@@ -57,17 +63,20 @@ __global__ void ar_advance_kernel(int32_t *st, const int64_t *tokens, int B, int
 // (transformer/mingpt.py:256-286, representers.py:187-196,432-442) computed in place.
 // One CTA per (row, position).  T positions starting at t0 (t0 read from st[ST_LEN]-1 when st != NULL).
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ar_embed_kernel(const int64_t *__restrict__ tokens, const float *__restrict__ emb0,
+__global__ void __launch_bounds__(256) ar_embed_kernel(const int64_t *tokens, const float *__restrict__ emb0,
                                                        const float *__restrict__ emb1, const float *__restrict__ embx,
                                                        const float *__restrict__ pos_emb,
-                                                       const float *__restrict__ cond_pos_emb, float *__restrict__ x,
+                                                       const float *__restrict__ cond_pos_emb, float *x,
                                                        int d, int max_len, int t0_arg, int T, int L_cond_arg,
-                                                       int64_t end0, const int32_t *__restrict__ st) {
-    const int b = blockIdx.y;
+                                                       int64_t end0, const int32_t *st, const int32_t *rowmap) {
+    pdl_trigger();
+    pdl_wait();
+    const int b = blockIdx.y;                      // compact row (index into x)
+    const int br = rowmap ? rowmap[b] : b;         // row of the token buffer
     const int t0 = st ? st[ST_LEN] - 1 : t0_arg;
     const int L_cond = st ? st[ST_LCOND] : L_cond_arg;
     const int t = t0 + blockIdx.x;
-    const int64_t *row = tokens + (size_t)b * max_len * 2;
+    const int64_t *row = tokens + (size_t)br * max_len * 2;
     const int64_t pos = row[2 * t], val = row[2 * t + 1];
     int64_t extra;
     if (t < L_cond) {
@@ -100,14 +109,17 @@ __global__ void __launch_bounds__(256) ar_embed_kernel(const int64_t *__restrict
 
 // x_out[b, i] = x_in[b, i] + emb0[tokens[b][t(b,i) + 1][0]]   ("x = x + tok_embs[0](target)", mingpt.py:309)
 // x_out rows are laid out (b, i) with i < T, x_in rows (b, i) with row stride Tin; source position t = t0 + i.
-__global__ void __launch_bounds__(256) ar_add_target_kernel(const float *__restrict__ x_in, float *__restrict__ x_out,
-                                                            const int64_t *__restrict__ tokens,
+__global__ void __launch_bounds__(256) ar_add_target_kernel(const float *x_in, float *x_out,
+                                                            const int64_t *tokens,
                                                             const float *__restrict__ emb0, int d, int max_len, int t0_arg,
-                                                            int T, int Tin, const int32_t *__restrict__ st) {
+                                                            int T, int Tin, const int32_t *st, const int32_t *rowmap) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.y;
+    const int br = rowmap ? rowmap[b] : b;
     const int t0 = st ? st[ST_LEN] - 1 : t0_arg;
     const int t = t0 + blockIdx.x;
-    const int64_t tgt = tokens[((size_t)b * max_len + t + 1) * 2];
+    const int64_t tgt = tokens[((size_t)br * max_len + t + 1) * 2];
     const float *e = emb0 + (size_t)tgt * d;
     const float *xi = x_in + ((size_t)b * Tin + blockIdx.x) * d;
     float *xo = x_out + ((size_t)b * T + blockIdx.x) * d;
@@ -119,19 +131,23 @@ __global__ void __launch_bounds__(256) ar_add_target_kernel(const float *__restr
 }
 
 // out[b, :] = x[b, T-1, :]
-__global__ void ar_take_last_kernel(const float *__restrict__ x, float *__restrict__ out, int d, int T) {
+__global__ void ar_take_last_kernel(const float *x, float *out, int d, int T, const int32_t *rowmap) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x;
     const float *s = x + ((size_t)b * T + (T - 1)) * d;
-    float *o = out + (size_t)b * d;
+    float *o = out + (size_t)(rowmap ? rowmap[b] : b) * d;
     for (int i = threadIdx.x * 4; i < d; i += blockDim.x * 4) st4(o + i, ld4(s + i));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // LayerNorm (eps 1e-5, biased variance), one warp per row.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict__ x, const float *__restrict__ w,
-                                                        const float *__restrict__ bvec, float *__restrict__ y, int rows,
+__global__ void __launch_bounds__(256) layernorm_kernel(const float *x, const float *__restrict__ w,
+                                                        const float *__restrict__ bvec, float *y, int rows,
                                                         int d) {
+    pdl_trigger();
+    pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= rows) return;
     const float *xr = x + (size_t)warp * d;
@@ -172,9 +188,11 @@ constexpr int LIN_NT = 64, LIN_BK = 32, LIN_S = LIN_BK + 4, LIN_STAGES = 3;
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 
 template <int MI, int KSPLIT>
-__global__ void __launch_bounds__(256) linear_kernel(const float *__restrict__ x, const float *__restrict__ W,
+__global__ void __launch_bounds__(256) linear_kernel(const float *x, const float *__restrict__ W,
                                                      const float *__restrict__ bias, const float *residual, float *y,
                                                      int M, int N, int K, int act) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int MT = 16 * MI;
     extern __shared__ __align__(16) float lin_smem[];
     float *xs = lin_smem;                             // [STAGES][MT][S]
@@ -298,21 +316,8 @@ static int launch_linear_t(const float *x, const float *W, const float *bias, co
         SFB_CUDA_TRY(cudaFuncSetAttribute(linear_kernel<MI, KSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((N + LIN_NT - 1) / LIN_NT, (M + MT - 1) / MT, KSPLIT);
-    cfg.blockDim = dim3(256);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = KSPLIT;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    SFB_CUDA_TRY(cudaLaunchKernelEx(&cfg, linear_kernel<MI, KSPLIT>, x, W, bias, residual, y, M, N, K, act));
-    count_launches(1);
-    return SFB200_OK;
+    return launch_ex("linear", linear_kernel<MI, KSPLIT>, dim3((N + LIN_NT - 1) / LIN_NT, (M + MT - 1) / MT, KSPLIT), dim3(256), smem,
+                     stream, dim3(1, 1, KSPLIT), x, W, bias, residual, y, M, N, K, act);
 }
 
 template <int MI>
@@ -350,9 +355,11 @@ int launch_linear(const float *x, const float *W, const float *bias, const float
 // rows are read through L1, and a shuffle reduction finishes each dot product.  fp32 FFMA, deterministic order.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int MR>
-__global__ void __launch_bounds__(256) gemv_kernel(const float *__restrict__ x, const float *__restrict__ W,
+__global__ void __launch_bounds__(256) gemv_kernel(const float *x, const float *__restrict__ W,
                                                    const float *__restrict__ bias, const float *residual, float *y, int N,
                                                    int K, int act) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (n >= N) return;
@@ -399,12 +406,11 @@ int launch_gemv(const float *x, const float *W, const float *bias, const float *
     if (M < 1 || M > 4 || K % 4 != 0) return SFB200_E_ARG;
     const dim3 grid((N + 7) / 8);
     switch (M) {
-        case 1: gemv_kernel<1><<<grid, 256, 0, s>>>(x, W, bias, residual, y, N, K, act); break;
-        case 2: gemv_kernel<2><<<grid, 256, 0, s>>>(x, W, bias, residual, y, N, K, act); break;
-        case 3: gemv_kernel<3><<<grid, 256, 0, s>>>(x, W, bias, residual, y, N, K, act); break;
-        default: gemv_kernel<4><<<grid, 256, 0, s>>>(x, W, bias, residual, y, N, K, act); break;
+        case 1: return launch_ex("gemv", gemv_kernel<1>, grid, dim3(256), 0, s, dim3(1, 1, 1), x, W, bias, residual, y, N, K, act);
+        case 2: return launch_ex("gemv", gemv_kernel<2>, grid, dim3(256), 0, s, dim3(1, 1, 1), x, W, bias, residual, y, N, K, act);
+        case 3: return launch_ex("gemv", gemv_kernel<3>, grid, dim3(256), 0, s, dim3(1, 1, 1), x, W, bias, residual, y, N, K, act);
+        default: return launch_ex("gemv", gemv_kernel<4>, grid, dim3(256), 0, s, dim3(1, 1, 1), x, W, bias, residual, y, N, K, act);
     }
-    return check_launch("gemv");
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -429,8 +435,8 @@ __device__ __forceinline__ float half_warp_sum(float v) {
 }
 
 // Streams keys t = t_beg + g, t_beg + g + G, ... (< t_end) for key-group g of G; key t lives at kbase + t*kstride.
-__device__ __forceinline__ void attn_stream_keys(SoftState &st, const float4 q4, const float *__restrict__ kbase,
-                                                 const float *__restrict__ vbase, size_t kstride, int t_beg, int t_end,
+__device__ __forceinline__ void attn_stream_keys(SoftState &st, const float4 q4, const float *kbase,
+                                                 const float *vbase, size_t kstride, int t_beg, int t_end,
                                                  int g, int G, int c) {
     for (int r0 = t_beg; r0 < t_end; r0 += G * ATT_U) {
         float4 kk[ATT_U], vv[ATT_U];
@@ -499,10 +505,12 @@ __device__ __forceinline__ void attn_merge(const SoftState &st, int grp, int c, 
     }
 }
 
-__global__ void __launch_bounds__(128) attn_decode_kernel(const float *__restrict__ qkv, float *kcache, float *vcache,
-                                                          float *__restrict__ out, float *__restrict__ part, int H,
-                                                          int max_len, int pos_arg, const int32_t *__restrict__ st_dev,
+__global__ void __launch_bounds__(128) attn_decode_kernel(const float *qkv, float *kcache, float *vcache,
+                                                          float *out, float *part, int H,
+                                                          int max_len, int pos_arg, const int32_t *st_dev,
                                                           int n_split) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float sm[8 * MRG];
     const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z;
     const int pos = st_dev ? st_dev[ST_LEN] - 1 : pos_arg;
@@ -551,8 +559,10 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const float *__restric
     }
 }
 
-__global__ void __launch_bounds__(64) attn_combine_kernel(const float *__restrict__ part, float *__restrict__ out, int H,
+__global__ void __launch_bounds__(64) attn_combine_kernel(const float *part, float *out, int H,
                                                           int n_split) {
+    pdl_trigger();
+    pdl_wait();
     const int h = blockIdx.x, b = blockIdx.y, i = threadIdx.x;
     const float *p = part + (((size_t)b * H + h) * n_split) * 66;
     float M = -INFINITY;
@@ -569,9 +579,12 @@ __global__ void __launch_bounds__(64) attn_combine_kernel(const float *__restric
 
 // Causal prefill: qkv (B, T, 3d).  CTA = 8 warps = 8 consecutive queries of one (b, h); each warp streams keys
 // [0, tq] straight from the qkv buffer (the 8 warps share them through L1) and scatters its own k, v into the cache.
-__global__ void __launch_bounds__(256) attn_prefill_kernel(const float *__restrict__ qkv, float *kcache, float *vcache,
-                                                           float *__restrict__ out, int H, int T, int max_len) {
+__global__ void __launch_bounds__(256) attn_prefill_kernel(const float *qkv, float *kcache, float *vcache,
+                                                           float *out, int H, int T, int max_len, const int32_t *rowmap) {
+    pdl_trigger();
+    pdl_wait();
     const int h = blockIdx.x, b = blockIdx.y;
+    const int br = rowmap ? rowmap[b] : b;         // KV-cache row
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tq = blockIdx.z * 8 + warp;
     if (tq >= T) return;
@@ -582,7 +595,7 @@ __global__ void __launch_bounds__(256) attn_prefill_kernel(const float *__restri
     float4 q4 = ld4(rowb + (size_t)tq * rs + c * 4);
     q4.x *= 0.125f; q4.y *= 0.125f; q4.z *= 0.125f; q4.w *= 0.125f;
     if (half == 0) {
-        const size_t base = (((size_t)b * H + h) * (size_t)max_len + tq) * 64 + c * 4;
+        const size_t base = (((size_t)br * H + h) * (size_t)max_len + tq) * 64 + c * 4;
         st4(kcache + base, ld4(rowb + (size_t)tq * rs + d + c * 4));
         st4(vcache + base, ld4(rowb + (size_t)tq * rs + 2 * d + c * 4));
     }
@@ -643,6 +656,8 @@ struct SampleArgs {
 };
 
 __global__ void __launch_bounds__(SMP_THREADS) ar_sample_kernel(SampleArgs a) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char smp_smem[];
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smp_smem);   // [npad]
     float *ev = reinterpret_cast<float *>(smp_smem + (size_t)a.npad * 8);           // [npad] exp(l_i - l_0), sorted order
@@ -849,61 +864,82 @@ __global__ void __launch_bounds__(SMP_THREADS) ar_sample_kernel(SampleArgs a) {
     }
 }
 
+// Rows that share their conditioning with an earlier row (the reference expands one shape to sample_n identical rows,
+// shapeformer.py:229): copy the prefix K/V (T positions) of every block, and the blocks[0] output of the last position.
+// grid (H, n_dup, n_blocks * 2); per CTA one contiguous T*64-float run.
+__global__ void __launch_bounds__(256) kv_prefix_copy_kernel(float *kv, const int32_t *dst_rows, const int32_t *src_rows, int H,
+                                                             int max_len, int T, int64_t per_block /* floats per K (or V) */) {
+    pdl_trigger();
+    pdl_wait();
+    const int h = blockIdx.x, dst = dst_rows[blockIdx.y], src = src_rows[blockIdx.y];
+    float *base = kv + (size_t)blockIdx.z * per_block;
+    const float4 *s4 = reinterpret_cast<const float4 *>(base + ((size_t)src * H + h) * (size_t)max_len * 64);
+    float4 *d4 = reinterpret_cast<float4 *>(base + ((size_t)dst * H + h) * (size_t)max_len * 64);
+    for (int i = threadIdx.x; i < T * 16; i += 256) d4[i] = s4[i];
+}
+__global__ void __launch_bounds__(256) row_copy_kernel(float *x, const int32_t *dst_rows, const int32_t *src_rows, int d) {
+    pdl_trigger();
+    pdl_wait();
+    const float *s = x + (size_t)src_rows[blockIdx.x] * d;
+    float *o = x + (size_t)dst_rows[blockIdx.x] * d;
+    for (int i = threadIdx.x * 4; i < d; i += 1024) st4(o + i, ld4(s + i));
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------------------------------
 int launch_state_init(int32_t *st, int L_cond, cudaStream_t s) {
-    ar_state_init_kernel<<<1, 32, 0, s>>>(st, L_cond);
-    return check_launch("ar_state_init");
+    return launch_ex("ar_state_init", ar_state_init_kernel, dim3(1), dim3(32), 0, s, dim3(1, 1, 1), st, L_cond);
 }
 int launch_chunk_reset(int32_t *st, cudaStream_t s) {
-    ar_chunk_reset_kernel<<<1, 32, 0, s>>>(st);
-    return check_launch("ar_chunk_reset");
+    return launch_ex("ar_chunk_reset", ar_chunk_reset_kernel, dim3(1), dim3(32), 0, s, dim3(1, 1, 1), st);
 }
 int launch_advance(int32_t *st, const int64_t *tokens, int B, int max_len, int64_t end0, int64_t end1, cudaStream_t s) {
-    ar_advance_kernel<<<1, 128, 0, s>>>(st, tokens, B, max_len, end0, end1);
-    return check_launch("ar_advance");
+    return launch_ex("ar_advance", ar_advance_kernel, dim3(1), dim3(128), 0, s, dim3(1, 1, 1), st, tokens, B, max_len, end0, end1);
 }
 int launch_embed(const int64_t *tokens, const float *emb0, const float *emb1, const float *embx, const float *pos_emb,
                  const float *cond_pos_emb, float *x, int B, int d, int max_len, int t0, int T, int L_cond, int64_t end0,
-                 const int32_t *st, cudaStream_t s) {
+                 const int32_t *st, cudaStream_t s, const int32_t *rowmap) {
     if (T <= 0) return SFB200_OK;
-    ar_embed_kernel<<<dim3(T, B), 256, 0, s>>>(tokens, emb0, emb1, embx, pos_emb, cond_pos_emb, x, d, max_len, t0, T, L_cond,
-                                               end0, st);
-    return check_launch("ar_embed");
+    return launch_ex("ar_embed", ar_embed_kernel, dim3(T, B), dim3(256), 0, s, dim3(1, 1, 1), tokens, emb0, emb1, embx, pos_emb,
+                     cond_pos_emb, x, d, max_len, t0, T, L_cond, end0, st, rowmap);
 }
 int launch_add_target(const float *x_in, float *x_out, const int64_t *tokens, const float *emb0, int B, int d, int max_len,
-                      int t0, int T, const int32_t *st, cudaStream_t s, int Tin) {
+                      int t0, int T, const int32_t *st, cudaStream_t s, int Tin, const int32_t *rowmap) {
     if (T <= 0) return SFB200_OK;
-    ar_add_target_kernel<<<dim3(T, B), 256, 0, s>>>(x_in, x_out, tokens, emb0, d, max_len, t0, T, Tin, st);
-    return check_launch("ar_add_target");
+    return launch_ex("ar_add_target", ar_add_target_kernel, dim3(T, B), dim3(256), 0, s, dim3(1, 1, 1), x_in, x_out, tokens, emb0, d,
+                     max_len, t0, T, Tin, st, rowmap);
 }
-int launch_take_last(const float *x, float *out, int B, int d, int T, cudaStream_t s) {
-    ar_take_last_kernel<<<B, 256, 0, s>>>(x, out, d, T);
-    return check_launch("ar_take_last");
+int launch_take_last(const float *x, float *out, int B, int d, int T, cudaStream_t s, const int32_t *rowmap) {
+    return launch_ex("ar_take_last", ar_take_last_kernel, dim3(B), dim3(256), 0, s, dim3(1, 1, 1), x, out, d, T, rowmap);
 }
 int launch_layernorm(const float *x, const float *w, const float *b, float *y, int rows, int d, cudaStream_t s) {
     if (rows <= 0) return SFB200_OK;
     if (d % 4 != 0) return SFB200_E_ARG;
-    layernorm_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, w, b, y, rows, d);
-    return check_launch("layernorm");
+    return launch_ex("layernorm", layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, dim3(1, 1, 1), x, w, b, y, rows, d);
 }
 int launch_attn_decode(const float *qkv, float *kc, float *vc, float *out, float *part, int B, int H, int max_len, int pos,
                        const int32_t *st, int n_split, cudaStream_t s) {
     if (n_split < 1 || (n_split > 1 && !part)) return SFB200_E_ARG;
-    attn_decode_kernel<<<dim3(H, B, n_split), 128, 0, s>>>(qkv, kc, vc, out, part, H, max_len, pos, st, n_split);
-    SFB_TRY(check_launch("attn_decode"));
-    if (n_split > 1) {
-        attn_combine_kernel<<<dim3(H, B), 64, 0, s>>>(part, out, H, n_split);
-        SFB_TRY(check_launch("attn_combine"));
-    }
+    SFB_TRY(launch_ex("attn_decode", attn_decode_kernel, dim3(H, B, n_split), dim3(128), 0, s, dim3(1, 1, 1), qkv, kc, vc, out, part,
+                      H, max_len, pos, st, n_split));
+    if (n_split > 1)
+        SFB_TRY(launch_ex("attn_combine", attn_combine_kernel, dim3(H, B), dim3(64), 0, s, dim3(1, 1, 1), part, out, H, n_split));
     return SFB200_OK;
 }
 int launch_attn_prefill(const float *qkv, float *kc, float *vc, float *out, int B, int H, int T, int max_len,
-                        cudaStream_t s) {
+                        cudaStream_t s, const int32_t *rowmap) {
     if (T <= 0) return SFB200_OK;
-    attn_prefill_kernel<<<dim3(H, B, (T + 7) / 8), 256, 0, s>>>(qkv, kc, vc, out, H, T, max_len);
-    return check_launch("attn_prefill");
+    return launch_ex("attn_prefill", attn_prefill_kernel, dim3(H, B, (T + 7) / 8), dim3(256), 0, s, dim3(1, 1, 1), qkv, kc, vc, out, H,
+                     T, max_len, rowmap);
+}
+
+int launch_prefix_copy(float *kv, float *x0, const int32_t *dst_rows, const int32_t *src_rows, int n_dup, int H, int max_len, int T,
+                       int d, int n_blocks, int64_t per_block, cudaStream_t s) {
+    if (n_dup <= 0) return SFB200_OK;
+    SFB_TRY(launch_ex("kv_prefix_copy", kv_prefix_copy_kernel, dim3(H, n_dup, n_blocks * 2), dim3(256), 0, s, dim3(1, 1, 1), kv,
+                      dst_rows, src_rows, H, max_len, T, per_block));
+    return launch_ex("row_copy", row_copy_kernel, dim3(n_dup), dim3(256), 0, s, dim3(1, 1, 1), x0, dst_rows, src_rows, d);
 }
 
 int launch_sample(const SampleLaunch &p, cudaStream_t s) {
@@ -924,8 +960,7 @@ int launch_sample(const SampleLaunch &p, cudaStream_t s) {
         SFB_CUDA_TRY(cudaFuncSetAttribute(ar_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12));
         attr_done = true;
     }
-    ar_sample_kernel<<<p.B, SMP_THREADS, smem, s>>>(a);
-    return check_launch("ar_sample");
+    return launch_ex("ar_sample", ar_sample_kernel, dim3(p.B), dim3(SMP_THREADS), smem, s, dim3(1, 1, 1), a);
 }
 
 }  // namespace sfb

@@ -1,5 +1,6 @@
 // extern "C" surface of libsfb200 (declared in include/sfb200.h); thin argument checks + dispatch to the launchers.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ar_kernels.cuh"
@@ -10,6 +11,14 @@ namespace sfb {
 static std::atomic<long long> g_launches{0};
 void count_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 static thread_local char g_err[512] = "";
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SFB200_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;   // on by default; SFB200_PDL=0 disables
+    }
+    return v == 1;
+}
 void set_cuda_error(cudaError_t e, const char *where) {
     snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
 }

@@ -38,6 +38,51 @@ static inline int check_launch(const char *where) {
         if (_r != SFB200_OK) return _r; \
     } while (0)
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------------
+// Every kernel of the AR step starts with pdl_trigger() + pdl_wait(): the NEXT kernel of the stream may be scheduled as soon
+// as all CTAs of this one have started (its launch latency and prologue overlap this kernel's execution), and it blocks in
+// pdl_wait() until this kernel has completed and its writes are visible.  Both are no-ops without the launch attribute.
+// NOTE: activations produced by the previous kernel must be read with coherent loads — no `const __restrict__` / __ldg on
+// them (an early-resident CTA could otherwise hit stale lines through the non-coherent path); only weights keep __restrict__.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+bool pdl_enabled();   // on by default; SFB200_PDL=0 in the environment disables the launch attribute
+
+// Launch with optional cluster dimensions and the PDL attribute.
+template <typename... KArgs, typename... Args>
+static inline int launch_ex(const char *what, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            dim3 cluster, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cluster.x * cluster.y * cluster.z > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = cluster.x;
+        attr[na].val.clusterDim.y = cluster.y;
+        attr[na].val.clusterDim.z = cluster.z;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_cuda_error(e, what);
+        return SFB200_E_CUDA;
+    }
+    count_launches(1);
+    return SFB200_OK;
+}
+
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }

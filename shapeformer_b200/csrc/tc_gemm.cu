@@ -53,7 +53,7 @@ __device__ __forceinline__ float gelu_erf_tc(float v) { return 0.5f * v * (1.0f 
 
 template <int BN>
 __global__ void __launch_bounds__(TCG_THREADS, 1)
-tc_linear_kernel(const float *__restrict__ x, const float *__restrict__ W, const float *__restrict__ bias,
+tc_linear_kernel(const float *x, const float *__restrict__ W, const float *__restrict__ bias,
                  const float *residual, float *y, int M, int N, int K, int act, int splits) {
     using L = TcgSmem<BN>;
     constexpr int TCG_NS = L::NS;
@@ -65,6 +65,7 @@ tc_linear_kernel(const float *__restrict__ x, const float *__restrict__ W, const
     uint64_t *dfree = dfull + 2;                                              // [2]  D[b] drained
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(dfree + 2);
 
+    pdl_trigger();
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row = tid & 127, half = (tid >> 7) & 1;   // split warps: W row / TMEM lane, and which half of K (and of D columns)
     const int n0 = blockIdx.x * 128, m0 = blockIdx.z * BN, sp = blockIdx.y;
@@ -94,7 +95,7 @@ tc_linear_kernel(const float *__restrict__ x, const float *__restrict__ W, const
 
     if (warp < 8) {
         // ================================ load + split + promote warps ================================
-        auto issue_loads = [&](int c, int s) {
+        auto issue_w = [&](int c, int s) {
             const int k0 = (c_beg + c) * 32;
             float *wdst = reinterpret_cast<float *>(smem + L::OFF_W + s * L::W_TILE);
 #pragma unroll
@@ -103,6 +104,9 @@ tc_linear_kernel(const float *__restrict__ x, const float *__restrict__ W, const
                 const float *src = W + (size_t)(n < N ? n : N - 1) * K + k0 + ch * 4;
                 cp_async16(wdst + r * 32 + ((ch ^ (r & 7)) << 2), src, n < N ? 16 : 0);
             }
+        };
+        auto issue_x = [&](int c, int s) {
+            const int k0 = (c_beg + c) * 32;
             float *xdst = reinterpret_cast<float *>(smem + L::OFF_X + s * L::X_TILE);
 #pragma unroll
             for (int j = 0; j < BN / 32; ++j) {
@@ -128,15 +132,23 @@ tc_linear_kernel(const float *__restrict__ x, const float *__restrict__ W, const
             tc_fence_before();
             mbar_arrive(&dfree[b]);
         };
+        // the weights do not depend on the previous kernel: start streaming them before the programmatic-dependency wait
+#pragma unroll
+        for (int c = 0; c < TCG_NS - 1; ++c)
+            if (c < nch) issue_w(c, c);
+        pdl_wait();
 #pragma unroll
         for (int c = 0; c < TCG_NS - 1; ++c) {
-            if (c < nch) issue_loads(c, c);
-            cp_async_commit();
+            if (c < nch) issue_x(c, c);
+            cp_async_commit();     // group 0 also carries every prologue W copy
         }
         for (int i = 0; i < nch; ++i) {
             cp_async_wait<TCG_NS - 2>();     // this thread's copies of chunk i have landed
             bar_sync(1, TCG_SPLIT);          // ... everybody's; and everybody finished splitting chunk i-1
-            if (i + TCG_NS - 1 < nch) issue_loads(i + TCG_NS - 1, (i + TCG_NS - 1) % TCG_NS);
+            if (i + TCG_NS - 1 < nch) {
+                issue_w(i + TCG_NS - 1, (i + TCG_NS - 1) % TCG_NS);
+                issue_x(i + TCG_NS - 1, (i + TCG_NS - 1) % TCG_NS);
+            }
             cp_async_commit();
             const int slot = i % TCG_NT;
             if (i >= TCG_NT) mbar_wait(&done[slot], ((i / TCG_NT) - 1) & 1);   // MMAs of chunk i-NT released the slot
@@ -186,6 +198,7 @@ tc_linear_kernel(const float *__restrict__ x, const float *__restrict__ W, const
         drain(ngroups - 1);
     } else {
         // ================================ MMA issuer (one elected thread of warp 4) ================================
+        pdl_wait();
         if ((tid & 31) == 0) {   // warp 8
             const uint32_t xh0 = smem_u32(smem + L::OFF_XH), xl0 = smem_u32(smem + L::OFF_XL);
             for (int i = 0; i < nch; ++i) {
@@ -332,21 +345,8 @@ static int launch_tc_t(const float *x, const float *W, const float *bias, const 
         attr_done = true;
     }
     const int splits = tc_pick_splits<BN>(M, N, K);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(n_tiles, splits, m_tiles);
-    cfg.blockDim = dim3(TCG_THREADS);
-    cfg.dynamicSmemBytes = TcgSmem<BN>::TOTAL;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1;
-    attr[0].val.clusterDim.y = splits;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    SFB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_linear_kernel<BN>, x, W, bias, residual, y, M, N, K, act, splits));
-    count_launches(1);
-    return SFB200_OK;
+    return launch_ex("tc_linear", tc_linear_kernel<BN>, dim3(n_tiles, splits, m_tiles), dim3(TCG_THREADS), TcgSmem<BN>::TOTAL, stream,
+                     dim3(1, splits, 1), x, W, bias, residual, y, M, N, K, act, splits);
 }
 
 int launch_linear_tc(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,

@@ -2,7 +2,8 @@
 codebook gather -> UNet3D + Upsampler conv prologue -> fused per-point kernel (trilinear feature sampling + ResNet-FC MLP).
 
 The gather, the layout change and the per-point kernel are libsfb200 kernels.  The conv prologue (SURVEY.md §8a row D1:
-"cuDNN first, custom later") runs the reference's own op set through PyTorch/cuDNN in strict fp32 (TF32 off).
+"cuDNN first, custom later") runs the reference's own op set through PyTorch/cuDNN: strict fp32 for the UNet3D, and for
+the Upsampler (80 % of the conv time) three TF32 tensor-core convolutions on hi/lo operand splits (fp32-grade results).
 """
 import torch
 import torch.nn.functional as F
@@ -24,41 +25,69 @@ def pack_mlp_weights(sd, prefix="decoder."):
     return flat
 
 
-def _gcr(sd, pre, x):
-    """'gcr' SingleConv (vqdif/unet3d.py:18-92)."""
-    x = F.group_norm(x, 8, sd[pre + "groupnorm.weight"], sd[pre + "groupnorm.bias"], 1e-5)
-    return F.relu_(F.conv3d(x, sd[pre + "conv.weight"], None, padding=1))
+def split_tf32(t):
+    """fp32 tensor -> (hi, lo) both exactly representable in TF32 (round-to-nearest on the 13 dropped mantissa bits):
+    t == hi + lo up to 2^-22 |t|."""
+    hi = ((t.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    lo = t - hi
+    lo = ((lo.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    return hi, lo
 
 
-def _crg(sd, pre, x):
-    """'crg' ConvLayer (vqdif/updown.py:79-99)."""
-    x = F.relu_(F.conv3d(x, sd[pre + "conv.weight"], None, padding=1))
-    return F.group_norm(x, 8, sd[pre + "groupnorm.weight"], sd[pre + "groupnorm.bias"], 1e-5)
+def _conv3(x, w, w_split, mode):
+    """3x3x3 conv, padding 1, no bias.  mode "fp32": one strict-fp32 cuDNN conv.  mode "3xtf32": the operands are split
+    into TF32 hi/lo parts and three TENSOR-CORE convs are summed (lo*hi + hi*lo + hi*hi, fp32 accumulate) — fp32-grade
+    results (measured 1-4e-5 abs on O(1) outputs vs 1e-3 for plain TF32) at 4-6x the speed of cuDNN's fp32 SIMT kernels."""
+    if mode == "fp32":
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            return F.conv3d(x, w, None, padding=1)
+    xh, xl = split_tf32(x)
+    wh, wl = w_split
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=True):
+        y = F.conv3d(xl, wh, None, padding=1)
+        y += F.conv3d(xh, wl, None, padding=1)
+        y += F.conv3d(xh, wh, None, padding=1)
+    return y
 
 
-def conv_prologue(sd, x, prefix="decoder."):
-    """UNet3D (3 levels, DoubleConv 'gcr', max-pool 2, nearest up + concat, 1x1 final conv — vqdif/unet3d.py:449-474)
-    followed by the Upsampler (2 x [nearest x2, 'crg', 'crg'] — vqdif/updown.py:119-132), strict fp32."""
+def conv_prologue(sd, x, prefix="decoder.", wsplit=None, unet_mode="fp32", up_mode="3xtf32"):
+    """UNet3D (3 levels, DoubleConv 'gcr' = GroupNorm(8) -> conv -> ReLU, max-pool 2, nearest up + concat, 1x1 final conv —
+    vqdif/unet3d.py:449-474) followed by the Upsampler (2 x [nearest x2, 'crg', 'crg'] = conv -> ReLU -> GroupNorm —
+    vqdif/updown.py:119-132).  `wsplit`: {conv weight key: (hi, lo)} for the layers run in 3xtf32 mode."""
+    wsplit = wsplit or {}
+
+    def conv(key, x, mode):
+        w = sd[key]
+        return _conv3(x, w, wsplit.get(key) or (split_tf32(w) if mode != "fp32" else None), mode)
+
+    def gcr(pre, x):
+        x = F.group_norm(x, 8, sd[pre + "groupnorm.weight"], sd[pre + "groupnorm.bias"], 1e-5)
+        return F.relu_(conv(pre + "conv.weight", x, unet_mode))
+
+    def crg(pre, x):
+        x = F.relu_(conv(pre + "conv.weight", x, up_mode))
+        return F.group_norm(x, 8, sd[pre + "groupnorm.weight"], sd[pre + "groupnorm.bias"], 1e-5)
+
     u = prefix + "unet3d."
+    feats = []
+    for i in range(3):
+        if i > 0:
+            x = F.max_pool3d(x, 2)
+        x = gcr(f"{u}encoders.{i}.basic_module.SingleConv1.", x)
+        x = gcr(f"{u}encoders.{i}.basic_module.SingleConv2.", x)
+        feats.insert(0, x)
+    for i, skip in enumerate(feats[1:]):
+        x = F.interpolate(x, size=skip.shape[2:], mode="nearest")
+        x = torch.cat([skip, x], 1)
+        x = gcr(f"{u}decoders.{i}.basic_module.SingleConv1.", x)
+        x = gcr(f"{u}decoders.{i}.basic_module.SingleConv2.", x)
     with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-        feats = []
-        for i in range(3):
-            if i > 0:
-                x = F.max_pool3d(x, 2)
-            x = _gcr(sd, f"{u}encoders.{i}.basic_module.SingleConv1.", x)
-            x = _gcr(sd, f"{u}encoders.{i}.basic_module.SingleConv2.", x)
-            feats.insert(0, x)
-        for i, skip in enumerate(feats[1:]):
-            x = F.interpolate(x, size=skip.shape[2:], mode="nearest")
-            x = torch.cat([skip, x], 1)
-            x = _gcr(sd, f"{u}decoders.{i}.basic_module.SingleConv1.", x)
-            x = _gcr(sd, f"{u}decoders.{i}.basic_module.SingleConv2.", x)
         x = F.conv3d(x, sd[u + "final_conv.weight"], sd[u + "final_conv.bias"])
-        up = prefix + "upsampler."
-        for s in range(2):
-            x = F.interpolate(x, scale_factor=2, mode="nearest")
-            x = _crg(sd, f"{up}blocks.{3 * s + 1}.", x)
-            x = _crg(sd, f"{up}blocks.{3 * s + 2}.", x)
+    up = prefix + "upsampler."
+    for s in range(2):
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+        x = crg(f"{up}blocks.{3 * s + 1}.", x)
+        x = crg(f"{up}blocks.{3 * s + 2}.", x)
     return x
 
 
@@ -67,7 +96,8 @@ class ImplicitDecoder:
     impl: 0 = tcgen05 tensor-core point kernel (default), 1 = fp32 FFMA point kernel (kept for cross-checking)."""
     _active = None   # which instance's MLP weights currently sit in the library's constant bank
 
-    def __init__(self, sd, device, impl=0, prefix="decoder.", codebook_key="quantizer.embedding.weight"):
+    def __init__(self, sd, device, impl=0, prefix="decoder.", codebook_key="quantizer.embedding.weight", unet_mode="fp32",
+                 up_mode="3xtf32"):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -77,6 +107,12 @@ class ImplicitDecoder:
                    if k.startswith(prefix) or k == codebook_key}
         self.codebook = self.sd[codebook_key]
         self.mlp = pack_mlp_weights(self.sd, prefix).to(self.device).contiguous()
+        self.unet_mode, self.up_mode = unet_mode, up_mode
+        self.wsplit = {}
+        for k, v in self.sd.items():
+            three = ("upsampler." in k and up_mode != "fp32") or ("unet3d." in k and unet_mode != "fp32")
+            if k.endswith("conv.weight") and v.dim() == 5 and v.shape[-1] == 3 and three:
+                self.wsplit[k] = split_tf32(v)
 
     def _activate(self):
         if ImplicitDecoder._active is not self:
@@ -97,7 +133,7 @@ class ImplicitDecoder:
 
     def feature_grid(self, quant_feat):
         """(B,128,16,16,16) quantised features -> channel-last (B,64,64,64,32) decoder feature grid."""
-        g = conv_prologue(self.sd, quant_feat, self.prefix).contiguous()
+        g = conv_prologue(self.sd, quant_feat, self.prefix, self.wsplit, self.unet_mode, self.up_mode).contiguous()
         B, C = g.shape[:2]
         S = g.shape[2] * g.shape[3] * g.shape[4]
         out = torch.empty(B, g.shape[2], g.shape[3], g.shape[4], C, dtype=torch.float32, device=self.device)

@@ -147,7 +147,7 @@ def test_full_64cubed_decode_properties(cuda, impl):
         occ = dec.occupancy(code, Xtg)
         assert (occ - torch.sigmoid(full[..., 0])).abs().max() < 1e-6
     alone = dec.decode_index(code[1:], Xtg)["logits"]
-    assert (full[1] - alone[0]).abs().max() < 1e-5     # cuDNN may pick another algorithm for B=1; MLP kernel is bitwise
+    assert (full[1] - alone[0]).abs().max() < 5e-5     # cuDNN may pick another algorithm for B=1; the point kernel is bitwise
     sel = torch.randperm(64 ** 3, generator=torch.Generator().manual_seed(1))[:4096]
     ref = O.decode_index(sd, code[:1], Xtg[:, sel])["logits"]
     assert (full[0, sel.to(cuda)].cpu() - ref[0]).abs().max() < 1e-4
@@ -175,3 +175,40 @@ def test_sampler_shipped_model_matches_oracle(cuda):
     print("shipped-size max |dlogit| =", worst)
     assert torch.equal(x.cpu(), ox)
     assert worst < 5e-5, worst
+
+
+def test_shared_conditioning_prefill_equals_per_row_prefill(cuda):
+    """Rows with identical conditioning share one prefill (leader + K/V prefix copy): same tokens, same logits."""
+    cfg = dict(synth.TINY_GPT, n_layers=(2, 2))
+    sd = synth.gpt_state_dict(cfg, seed=33, peaky=True)
+    base = synth.cond_indices(3, 21, seed=6)
+    c = base[[0, 0, 1, 0, 1, 2, 2]]          # groups {0,1,3}, {2,4}, {5,6}
+    B, steps = c.shape[0], 8
+    noise = util.noise_from_seed(2, steps, B, 4097)
+    s = make_sampler(cuda, cfg, sd, B, 21, steps, prefill_tokens=2 * 21)
+    outs = []
+    for share in (False, True):
+        x, hist = s.sample(c, steps, top_k=40, top_p=0.8, best_in_first=True, mask_invalid=True,
+                           mask_invalid_completion=True, noise=noise, share_prefix=share, stop_early=False)
+        outs.append((x.cpu().clone(), [h.cpu().clone() for h in hist]))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1], outs[1][1]):
+        fin = torch.isfinite(a)
+        assert torch.equal(fin, torch.isfinite(b)) and (a[fin] - b[fin]).abs().max() < 2e-5
+    ox, _ = O.sample_indices(sd, O.GPTSpec(**cfg), c, c[:, :0], steps, END, True, 40, 0.8, 1.0, True, True,
+                             noise=O.ListNoise(noise.reshape(-1, B, 4097)), cached=True)
+    assert torch.equal(outs[1][0][:, :ox.shape[1]], ox)
+
+
+@pytest.mark.parametrize("unet_mode,up_mode", [("fp32", "fp32"), ("fp32", "3xtf32"), ("3xtf32", "3xtf32")])
+def test_conv_prologue_precision_modes(cuda, unet_mode, up_mode):
+    """The 3xTF32 tensor-core convolutions keep the decoded logits within the 1e-4 budget (plain TF32 does not)."""
+    sd = synth.vqdif_state_dict(seed=4)
+    code = synth.code_grids(2, seed=3)
+    Xtg = torch.rand(1, 20000, 3, generator=torch.Generator().manual_seed(0)) * 2 - 1
+    ref = O.decode_index(sd, code, Xtg.expand(2, -1, -1))["logits"][..., 0]
+    dec = decoder.ImplicitDecoder(sd, cuda, unet_mode=unet_mode, up_mode=up_mode)
+    out = dec.decode_index(code, Xtg)["logits"][..., 0].cpu()
+    err = (out - ref).abs().max().item()
+    print(f"conv modes unet={unet_mode} upsampler={up_mode}: max |dlogit| = {err:.2e}")
+    assert err < 1e-4, err
