@@ -251,13 +251,8 @@ def main():
         model.transformer.load_state_dict(gpt_sd)
         vq.load_state_dict(vq_sd, strict=False)
     model.to(dev); vq.to(dev)
-    if world > 1:
-        flat = torch.cat([p.data.reshape(-1) for p in list(model.transformer.parameters()) + list(vq.parameters())])
-        dist.broadcast(flat, 0)
-        o = 0
-        for p in list(model.transformer.parameters()) + list(vq.parameters()):
-            p.data.copy_(flat[o:o + p.numel()].view_as(p)); o += p.numel()
-        del flat
+    from shapeformer_b200 import dist as sdist
+    sdist.broadcast_parameters([p.data for p in list(model.transformer.parameters()) + list(vq.parameters())], src=0)
     model.representer.vqvae_model = vq
     model.history_device = None     # value arm: history stays off; the e2e arm turns the reference's CPU history on
 
