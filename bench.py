@@ -22,6 +22,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# keep stdout to the single JSON line the driver parses: NCCL prints its version banner there when NCCL_DEBUG=VERSION/INFO
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("SFB200_KEEP_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import torch  # noqa: E402
 
 END = (4096, 4096)
@@ -317,8 +321,9 @@ def main():
                    mask_invalid_completion=False, use_graph=False, stop_early=False)
     pe1.record()
     torch.cuda.synchronize()
-    a_ms, a_n, a_b = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
-    _lib.check(lib.sfb200_ar_profile_read(sampler.handle, ctypes.byref(a_ms), ctypes.byref(a_n), ctypes.byref(a_b)))
+    a_ms, a_n, a_b, a_br = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double(), ctypes.c_double()
+    _lib.check(lib.sfb200_ar_profile_read(sampler.handle, ctypes.byref(a_ms), ctypes.byref(a_n), ctypes.byref(a_b),
+                                          ctypes.byref(a_br)))
     _lib.check(lib.sfb200_ar_profile(sampler.handle, 0))
     peak, how = measured_peaks()
     if a_n.value:
@@ -328,6 +333,10 @@ def main():
                 "peak_source": how + "; sustained-style figure (kernel timed inside a long step)",
                 "launches": a_n.value, "avg_launch_us": 1e3 * a_ms.value / a_n.value,
                 "algorithmic_bytes_per_launch": a_b.value / a_n.value,
+                "per_row_formula_bytes_per_launch": a_br.value / a_n.value,
+                "per_row_formula_gbs": a_br.value / (a_ms.value * 1e-3) / 1e9,
+                "note": "achieved = bytes that must move / time: the conditioning-prefix K/V of the sample_n rows of a shape is "
+                        "read once per shape (SURVEY §7 item 5); per_row_formula_* applies SURVEY §8d's per-row byte count",
                 "share_of_ar_pass": a_ms.value / pe0.elapsed_time(pe1),
                 "how": "CUDA events around every attention launch of one eager AR pass over the same batch, right after the "
                        "timed region (the timed region replays the step as a CUDA graph, where events cannot be read)"}

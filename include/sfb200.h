@@ -173,9 +173,11 @@ const int32_t *sfb200_ar_status_ptr(const sfb200_ar *h);
 /* Measurement aid for bench.py: when enabled (eager stepping only), every attention launch of sfb200_ar_steps is bracketed
  * by CUDA events on `stream`.  sfb200_ar_profile_read must be called after the stream has been synchronised; it returns the
  * summed device time (ms), the number of launches and the ALGORITHMIC bytes of those launches
- * (per launch: B * [2*pos*d*4 (K,V read) + 2*d*4 (append) + 2*d*4 (q in, out)]) and resets the counters. */
+ * (per launch: key rows * 2*d*4 (K,V read) + B * [2*d*4 (append) + 2*d*4 (q in, out)]; key rows = B*pos, or
+ * with conditioning-prefix sharing L_cond per group + (pos - L_cond) per row) and resets the counters. */
 int sfb200_ar_profile(sfb200_ar *h, int enable);
-int sfb200_ar_profile_read(sfb200_ar *h, double *attn_ms, int64_t *attn_launches, double *attn_bytes);
+int sfb200_ar_profile_read(sfb200_ar *h, double *attn_ms, int64_t *attn_launches, double *attn_bytes,
+                           double *attn_bytes_per_row /* may be NULL: SURVEY per-row formula without prefix sharing */);
 
 /* ---- individual AR operators (exposed for parity tests and profiling; the same kernels the calls above enqueue) ---- */
 

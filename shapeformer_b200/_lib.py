@@ -63,7 +63,7 @@ SIGNATURES = {
     "sfb200_ar_status_ptr": (vp, [vp]),
     "sfb200_ar_profile": (ctypes.c_int, [vp, ctypes.c_int]),
     "sfb200_ar_profile_read": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
-                                              ctypes.POINTER(ctypes.c_double)]),
+                                              ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "sfb200_linear": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
     "sfb200_linear_tc": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
     "sfb200_layernorm": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp]),

@@ -126,13 +126,14 @@ struct sfb200_ar {
     int Vmax;
     // per batch
     int B, L_cond, n_split;
+    int attn_group;            // > 1: contiguous groups of this many rows share their conditioning prefix K/V
     bool begun;
     sfb200_ar_sampling sp;
     // graph
     cudaGraphExec_t gexec;
     cudaStream_t cap_stream;   // private stream used only to record the step graph (the legacy default stream cannot capture)
     const float *g_noise;
-    int g_B;
+    int g_B, g_group;
     sfb200_ar_sampling g_sp;
     long long g_nodes;         // kernel nodes in the captured step
     bool capturing;
@@ -140,7 +141,8 @@ struct sfb200_ar {
     bool prof;
     std::vector<cudaEvent_t> *ev;
     size_t ev_used;
-    double prof_bytes;
+    double prof_bytes;         // bytes that must move (conditioning prefix counted once per group when shared)
+    double prof_bytes_per_row; // SURVEY §8d per-row formula (no sharing)
     int steps_host;            // steps enqueued since sfb200_ar_begin (host mirror of st[ST_STEPS])
 };
 
@@ -272,14 +274,20 @@ static int block_step(sfb200_ar *h, int g, int l, float *x, cudaStream_t s) {
         SFB_CUDA_TRY(cudaEventRecord((*h->ev)[h->ev_used], s));
     }
     SFB_TRY(launch_attn_decode(qkv, kcache(h, g, l, 0), vcache(h, g, l, 0), att, part, B, H, h->cfg.max_len, 0, st,
-                               h->n_split, s));
+                               h->n_split, s, h->attn_group, 0, g == 1 ? -1 : 0));
     if (timed) {
         SFB_CUDA_TRY(cudaEventRecord((*h->ev)[h->ev_used + 1], s));
         h->ev_used += 2;
         // position of this launch = L-1: blocks[1] runs before the step's advance (L = L_cond + j), blocks[0] after it
         // (L = L_cond + j + 1, and steps_host has already been incremented)
         const double pos = (double)(h->L_cond + h->steps_host) - 1.0;
-        h->prof_bytes += (double)B * (2.0 * pos * d * 4.0 + 4.0 * d * 4.0);
+        // key rows that must be read: per row `pos`, or with prefix sharing the shared prefix once per group + own keys
+        const double lc = (double)h->L_cond - (g == 1 ? 1.0 : 0.0);
+        const double shared = pos < lc ? pos : lc;
+        const double key_rows = h->attn_group > 1 ? (double)(B / h->attn_group) * shared + (double)B * (pos - shared)
+                                                  : (double)B * pos;
+        h->prof_bytes += key_rows * 2.0 * d * 4.0 + (double)B * 4.0 * d * 4.0;
+        h->prof_bytes_per_row += (double)B * (2.0 * pos * d * 4.0 + 4.0 * d * 4.0);
     }
     SFB_TRY(linear(h, att, W_(h, SFB200_W_PROJ_W, g, l), W_(h, SFB200_W_PROJ_B, g, l), x, x, B, d, d, 0, s));
     SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN2_W, g, l), W_(h, SFB200_W_LN2_B, g, l), hb, B, d, s));
@@ -316,6 +324,14 @@ extern "C" int sfb200_ar_begin_shared(sfb200_ar *h, int B, int L_cond, const sfb
         if (src == b) lead.push_back(b); else { dup_dst.push_back(b); dup_src.push_back(src); }
     }
     const int n_lead = (int)lead.size(), n_dup = (int)dup_dst.size();
+    // contiguous groups of equal size (the reference's c_indices.expand(sample_n)) enable the grouped attention kernel
+    h->attn_group = 1;
+    for (int G = 8; G >= 2; G -= 2) {
+        if (B % G != 0 || !row_src) continue;
+        bool ok = true;
+        for (int b = 0; b < B && ok; ++b) ok = row_src[b] == (b / G) * G;
+        if (ok) { h->attn_group = G; break; }
+    }
     int32_t *rm = WS_<int32_t>(h, h->buf.rowmap);
     const int32_t *rm_lead = nullptr, *rm_dst = rm + h->cfg.max_rows, *rm_src = rm + 2 * h->cfg.max_rows;
     if (n_dup > 0) {
@@ -406,7 +422,8 @@ extern "C" int sfb200_ar_steps(sfb200_ar *h, int n_steps, const float *noise, in
     SFB_TRY(launch_chunk_reset(st, s));
     int done = 0;
     if (use_graph) {
-        const bool valid = h->gexec && h->g_noise == noise && h->g_B == h->B && same_sp(h->g_sp, h->sp);
+        const bool valid = h->gexec && h->g_noise == noise && h->g_B == h->B && same_sp(h->g_sp, h->sp) &&
+                           h->g_group == h->attn_group;
         if (!valid) {
             if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
             if (n_steps > 0) {   // first step eagerly: loads modules and sets function attributes outside capture
@@ -428,7 +445,7 @@ extern "C" int sfb200_ar_steps(sfb200_ar *h, int n_steps, const float *noise, in
             const cudaError_t ei = cudaGraphInstantiate(&h->gexec, graph, 0);
             cudaGraphDestroy(graph);
             SFB_CUDA_TRY(ei);
-            h->g_noise = noise; h->g_B = h->B; h->g_sp = h->sp;
+            h->g_noise = noise; h->g_B = h->B; h->g_sp = h->sp; h->g_group = h->attn_group;
         }
         for (; done < n_steps; ++done) {
             SFB_CUDA_TRY(cudaGraphLaunch(h->gexec, s));
@@ -446,10 +463,12 @@ extern "C" int sfb200_ar_profile(sfb200_ar *h, int enable) {
     h->prof = enable != 0;
     h->ev_used = 0;
     h->prof_bytes = 0.0;
+    h->prof_bytes_per_row = 0.0;
     return SFB200_OK;
 }
 
-extern "C" int sfb200_ar_profile_read(sfb200_ar *h, double *attn_ms, int64_t *attn_launches, double *attn_bytes) {
+extern "C" int sfb200_ar_profile_read(sfb200_ar *h, double *attn_ms, int64_t *attn_launches, double *attn_bytes,
+                                      double *attn_bytes_per_row) {
     if (!h || !attn_ms || !attn_launches || !attn_bytes) return SFB200_E_ARG;
     double ms = 0.0;
     for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
@@ -460,7 +479,9 @@ extern "C" int sfb200_ar_profile_read(sfb200_ar *h, double *attn_ms, int64_t *at
     *attn_ms = ms;
     *attn_launches = (int64_t)(h->ev_used / 2);
     *attn_bytes = h->prof_bytes;
+    if (attn_bytes_per_row) *attn_bytes_per_row = h->prof_bytes_per_row;
     h->ev_used = 0;
     h->prof_bytes = 0.0;
+    h->prof_bytes_per_row = 0.0;
     return SFB200_OK;
 }

@@ -419,7 +419,7 @@ int launch_gemv(const float *x, const float *W, const float *bias, const float *
 // q / k / v, so one key row (256 B) is one coalesced 16-lane float4 load; each half-warp keeps its own online-softmax
 // state (m, l, acc[4]) and the 8 states are merged through shared memory at the end.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int ATT_U = 4;  // keys in flight per half-warp
+constexpr int ATT_U = 6;  // keys in flight per half-warp
 
 struct SoftState {
     float m, l;
@@ -435,6 +435,9 @@ __device__ __forceinline__ float half_warp_sum(float v) {
 }
 
 // Streams keys t = t_beg + g, t_beg + g + G, ... (< t_end) for key-group g of G; key t lives at kbase + t*kstride.
+// STREAM: evict-first loads for data touched once per launch; otherwise default caching (lines shared by sibling CTAs stay
+// in L2 long enough to be hit).
+template <bool STREAM = true>
 __device__ __forceinline__ void attn_stream_keys(SoftState &st, const float4 q4, const float *kbase,
                                                  const float *vbase, size_t kstride, int t_beg, int t_end,
                                                  int g, int G, int c) {
@@ -446,8 +449,8 @@ __device__ __forceinline__ void attn_stream_keys(SoftState &st, const float4 q4,
             const int t = r0 + u * G + g;
             ok[u] = t < t_end;
             const size_t off = (size_t)(ok[u] ? t : t_beg) * kstride + c * 4;
-            kk[u] = ld4_stream(kbase + off);
-            vv[u] = ld4_stream(vbase + off);
+            kk[u] = STREAM ? ld4_stream(kbase + off) : ld4(kbase + off);
+            vv[u] = STREAM ? ld4_stream(vbase + off) : ld4(vbase + off);
         }
         float s[ATT_U];
         float mx = st.m;
@@ -508,7 +511,7 @@ __device__ __forceinline__ void attn_merge(const SoftState &st, int grp, int c, 
 __global__ void __launch_bounds__(128) attn_decode_kernel(const float *qkv, float *kcache, float *vcache,
                                                           float *out, float *part, int H,
                                                           int max_len, int pos_arg, const int32_t *st_dev,
-                                                          int n_split) {
+                                                          int n_split, int group, int lcond_arg, int lcond_delta) {
     pdl_trigger();
     pdl_wait();
     __shared__ __align__(16) float sm[8 * MRG];
@@ -542,7 +545,18 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const float *qkv, floa
     int per = (pos + n_split - 1) / n_split;
     per = (per + 7) & ~7;
     const int t_beg = min(sp * per, pos), t_end = min(t_beg + per, pos);
-    attn_stream_keys(st, q4, kcache + base, vcache + base, 64, t_beg, t_end, grp, 8, c);
+    // Rows of one shape (`group` consecutive rows, the reference's sample_n expansion) hold bit-identical K/V for the
+    // conditioning prefix: all of them read the LEADER's copy with default caching, so the sibling CTAs (adjacent block
+    // indices, scheduled together) hit each other's lines in L2 and the prefix crosses HBM once per shape.  blocks[1]'s
+    // position L_cond-1 already carries each row's own first sampled pos (lcond_delta = -1).
+    int shared_end = 0;
+    if (group > 1) shared_end = min((st_dev ? st_dev[ST_LCOND] : lcond_arg) + lcond_delta, pos);
+    const int a_end = min(t_end, max(shared_end, t_beg));
+    if (a_end > t_beg) {
+        const size_t lbase = ((size_t)((b / group) * group) * H + h) * (size_t)max_len * 64;
+        attn_stream_keys<false>(st, q4, kcache + lbase, vcache + lbase, 64, t_beg, a_end, grp, 8, c);
+    }
+    attn_stream_keys<true>(st, q4, kcache + base, vcache + base, 64, a_end, t_end, grp, 8, c);
 
     float M, Ls, o0, o1;
     attn_merge<8>(st, grp, c, sm, M, Ls, o0, o1);
@@ -919,10 +933,10 @@ int launch_layernorm(const float *x, const float *w, const float *b, float *y, i
     return launch_ex("layernorm", layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, dim3(1, 1, 1), x, w, b, y, rows, d);
 }
 int launch_attn_decode(const float *qkv, float *kc, float *vc, float *out, float *part, int B, int H, int max_len, int pos,
-                       const int32_t *st, int n_split, cudaStream_t s) {
-    if (n_split < 1 || (n_split > 1 && !part)) return SFB200_E_ARG;
+                       const int32_t *st, int n_split, cudaStream_t s, int group, int lcond, int lcond_delta) {
+    if (n_split < 1 || (n_split > 1 && !part) || group < 1 || B % group != 0) return SFB200_E_ARG;
     SFB_TRY(launch_ex("attn_decode", attn_decode_kernel, dim3(H, B, n_split), dim3(128), 0, s, dim3(1, 1, 1), qkv, kc, vc, out, part,
-                      H, max_len, pos, st, n_split));
+                      H, max_len, pos, st, n_split, group, lcond, lcond_delta));
     if (n_split > 1)
         SFB_TRY(launch_ex("attn_combine", attn_combine_kernel, dim3(H, B), dim3(64), 0, s, dim3(1, 1, 1), part, out, H, n_split));
     return SFB200_OK;

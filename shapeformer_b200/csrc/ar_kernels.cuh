@@ -38,7 +38,7 @@ int launch_linear(const float *x, const float *W, const float *bias, const float
 int launch_linear_tc(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
                      int act, cudaStream_t stream);
 int launch_attn_decode(const float *qkv, float *kc, float *vc, float *out, float *part, int B, int H, int max_len, int pos,
-                       const int32_t *st, int n_split, cudaStream_t s);
+                       const int32_t *st, int n_split, cudaStream_t s, int group = 1, int lcond = 0, int lcond_delta = 0);
 int launch_attn_prefill(const float *qkv, float *kc, float *vc, float *out, int B, int H, int T, int max_len,
                         cudaStream_t s, const int32_t *rowmap = nullptr);
 int launch_sample(const SampleLaunch &p, cudaStream_t s);

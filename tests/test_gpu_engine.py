@@ -177,12 +177,16 @@ def test_sampler_shipped_model_matches_oracle(cuda):
     assert worst < 5e-5, worst
 
 
-def test_shared_conditioning_prefill_equals_per_row_prefill(cuda):
-    """Rows with identical conditioning share one prefill (leader + K/V prefix copy): same tokens, same logits."""
+@pytest.mark.parametrize("pattern", [[0, 0, 1, 0, 1, 2, 2],          # scattered groups: shared prefill, per-row attention
+                                     [0, 0, 0, 0, 1, 1, 1, 1],       # contiguous groups of 4: grouped attention kernel
+                                     [0, 0, 1, 1, 2, 2]])            # contiguous groups of 2
+def test_shared_conditioning_prefill_equals_per_row_prefill(cuda, pattern):
+    """Rows with identical conditioning share one prefill (leader + K/V prefix copy) and, when the groups are contiguous,
+    one pass over the conditioning-prefix K/V in the decode attention: same tokens, same logits as the per-row path."""
     cfg = dict(synth.TINY_GPT, n_layers=(2, 2))
     sd = synth.gpt_state_dict(cfg, seed=33, peaky=True)
     base = synth.cond_indices(3, 21, seed=6)
-    c = base[[0, 0, 1, 0, 1, 2, 2]]          # groups {0,1,3}, {2,4}, {5,6}
+    c = base[pattern]
     B, steps = c.shape[0], 8
     noise = util.noise_from_seed(2, steps, B, 4097)
     s = make_sampler(cuda, cfg, sd, B, 21, steps, prefill_tokens=2 * 21)
