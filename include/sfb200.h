@@ -130,6 +130,9 @@ int64_t sfb200_ar_kv_bytes(const sfb200_ar_config *cfg);
 int64_t sfb200_ar_workspace_bytes(const sfb200_ar_config *cfg);
 int64_t sfb200_ar_history_floats(const sfb200_ar_config *cfg);  /* 0 when keep_history == 0 */
 
+/* floats of the optional pre-split copy of the transformer's GEMM weights (see sfb200_ar_set_pretiled) */
+int64_t sfb200_ar_pretiled_floats(const sfb200_ar_config *cfg);
+
 typedef struct sfb200_ar sfb200_ar;  /* host-side handle (small, malloc'ed); owns no device memory */
 
 /* Bind caller-owned device buffers.  weights: packed per sfb200_ar_weight_offset.  tokens: (max_rows, max_len, 2) int64
@@ -137,6 +140,10 @@ typedef struct sfb200_ar sfb200_ar;  /* host-side handle (small, malloc'ed); own
 int sfb200_ar_create(const sfb200_ar_config *cfg, const float *weights, void *kv_cache, void *workspace, int64_t *tokens,
                      float *history, sfb200_ar **out);
 void sfb200_ar_destroy(sfb200_ar *h);
+
+/* Optional: bind a caller-owned buffer of sfb200_ar_pretiled_floats(cfg) floats and fill it (on `stream`) with the pre-split
+ * TF32 tiles of every block / head weight.  Decode steps with 9..64 rows then use sfb200_linear_tc_ps. */
+int sfb200_ar_set_pretiled(sfb200_ar *h, float *pretiled, void *stream);
 
 typedef struct sfb200_ar_sampling {
     int top_k;                    /* <= 0 disables (common.py:265) */
@@ -190,6 +197,18 @@ int sfb200_linear(const float *x, const float *W, const float *bias, const float
  * three MMAs per product, TMEM accumulator promoted to fp32 registers every two K chunks, cluster (DSMEM) split-K. */
 int sfb200_linear_tc(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
                      int act, void *stream);
+
+/* Decode-step variant (M <= 64) reading PRE-SPLIT weight tiles: sfb200_tc_pretile rewrites W (N, K) as TF32 hi/lo tiles in the
+ * tensor core's shared-memory image (sfb200_tc_pretiled_floats(N, K) floats); sfb200_linear_tc_ps then streams each 32 KB
+ * (tile, K-chunk) with one TMA bulk copy and feeds both MMA operands from shared memory.  Same results as sfb200_linear_tc. */
+int64_t sfb200_tc_pretiled_floats(int N, int K);
+int sfb200_tc_pretile(const float *W, float *Wt, int N, int K, void *stream);
+int sfb200_linear_tc_ps(const float *x, const float *Wt, const float *bias, const float *residual, float *y, int M, int N, int K,
+                        int act, void *stream);
+
+/* Development aid: register a device buffer of 16 uint64; CTA (0,0) of sfb200_linear_tc_ps stamps %globaltimer (ns) at its
+ * phase boundaries (slots documented in tc_gemm_ps.cu).  NULL unregisters. */
+int sfb200_debug_ps_timeline(void *buf16);
 
 /* LayerNorm over the last dim, eps = 1e-5 (mingpt.py:97-98,224). */
 int sfb200_layernorm(const float *x, const float *w, const float *b, float *y, int rows, int d, void *stream);

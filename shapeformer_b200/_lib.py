@@ -55,6 +55,8 @@ SIGNATURES = {
     "sfb200_ar_kv_bytes": (ctypes.c_int64, [ctypes.POINTER(ArConfig)]),
     "sfb200_ar_workspace_bytes": (ctypes.c_int64, [ctypes.POINTER(ArConfig)]),
     "sfb200_ar_history_floats": (ctypes.c_int64, [ctypes.POINTER(ArConfig)]),
+    "sfb200_ar_pretiled_floats": (ctypes.c_int64, [ctypes.POINTER(ArConfig)]),
+    "sfb200_ar_set_pretiled": (ctypes.c_int, [vp, vp, vp]),
     "sfb200_ar_create": (ctypes.c_int, [ctypes.POINTER(ArConfig), vp, vp, vp, vp, vp, ctypes.POINTER(vp)]),
     "sfb200_ar_destroy": (None, [vp]),
     "sfb200_ar_begin": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ArSampling), vp]),
@@ -66,6 +68,10 @@ SIGNATURES = {
                                               ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "sfb200_linear": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
     "sfb200_linear_tc": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
+    "sfb200_tc_pretiled_floats": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int]),
+    "sfb200_tc_pretile": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp]),
+    "sfb200_linear_tc_ps": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
+    "sfb200_debug_ps_timeline": (ctypes.c_int, [vp]),
     "sfb200_layernorm": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp]),
     "sfb200_attn_decode": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,
                                           ctypes.c_int, vp]),

@@ -73,7 +73,7 @@ class ARSampler:
     """KV-cached sampler for up to `max_rows` rows.  Buffers are allocated once and reused across batches."""
 
     def __init__(self, weights_blob, spec, end_tokens=(4096, 4096), max_rows=1, max_cond=406, max_steps=512,
-                 keep_history=True, prefill_tokens=8192, chunk_steps=32, device=None):
+                 keep_history=True, prefill_tokens=8192, chunk_steps=32, device=None, pretile=True):
         self.lib = _lib.load()
         self.spec, self.end_tokens = dict(spec), tuple(int(e) for e in end_tokens)
         self.device = device or weights_blob.device
@@ -105,6 +105,13 @@ class ARSampler:
                    "sfb200_ar_create")
         self.handle = h
         self._status_ptr = self.lib.sfb200_ar_status_ptr(self.handle)
+        # batches of 9..64 rows run their linear layers from pre-split TF32 weight tiles (2x the GEMM weight bytes)
+        self.pretiled = None
+        if pretile and 9 <= max_rows <= 64:
+            n = self.lib.sfb200_ar_pretiled_floats(ctypes.byref(self.cfg))
+            self.pretiled = torch.empty(n, dtype=torch.float32, device=dev)
+            _lib.check(self.lib.sfb200_ar_set_pretiled(self.handle, _lib.ptr(self.pretiled), _lib.stream_ptr()),
+                       "sfb200_ar_set_pretiled")
 
     def __del__(self):
         try:

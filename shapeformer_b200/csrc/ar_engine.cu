@@ -119,6 +119,7 @@ struct sfb200_ar {
     Layout lay;
     Buffers buf;
     const float *w;
+    float *wt;                 // optional pre-split GEMM weight tiles (sfb200_ar_set_pretiled)
     char *ws;
     float *kv;
     int64_t *tokens;
@@ -230,11 +231,34 @@ const int32_t *sfb200_ar_status_ptr(const sfb200_ar *h) { return h ? WS_<int32_t
 
 }  // extern "C"
 
-// nn.Linear dispatch: tcgen05 3xTF32 kernel for M >= 9 rows, fp32 FFMA kernel for the smallest batches.
-static int linear(sfb200_ar *h, const float *x, const float *W, const float *bias, const float *residual, float *y, int M,
-                  int N, int K, int act, cudaStream_t s) {
-    if (M >= 9)
-        return launch_linear_tc(x, W, bias, residual, y, M, N, K, act, s);
+// Pre-split tile blob: per block [QKV | PROJ | FC1 | FC2], then the two heads.
+static int64_t wt_block_floats(const sfb200_ar_config *c) {
+    const int d = c->n_embd;
+    return tc_pretiled_floats(3 * d, d) + tc_pretiled_floats(d, d) + tc_pretiled_floats(4 * d, d) + tc_pretiled_floats(d, 4 * d);
+}
+static int64_t wt_offset(const sfb200_ar_config *c, int id, int g, int l) {
+    const int d = c->n_embd;
+    const int64_t nblocks = c->n_layers[0] + c->n_layers[1];
+    if (id == SFB200_W_HEAD_W) return nblocks * wt_block_floats(c) + (g == 1 ? tc_pretiled_floats(c->vocab[0], d) : 0);
+    int64_t o = ((g == 0 ? 0 : c->n_layers[0]) + l) * wt_block_floats(c);
+    if (id == SFB200_W_QKV_W) return o;
+    o += tc_pretiled_floats(3 * d, d);
+    if (id == SFB200_W_PROJ_W) return o;
+    o += tc_pretiled_floats(d, d);
+    if (id == SFB200_W_FC1_W) return o;
+    o += tc_pretiled_floats(4 * d, d);
+    if (id == SFB200_W_FC2_W) return o;
+    return -1;
+}
+
+// nn.Linear dispatch: 9..64 rows -> tcgen05 3xTF32 from pre-split tiles (when bound), else tcgen05 with in-kernel split;
+// <= 8 rows -> GEMV / FFMA kernels on the fp32 weights.
+static int linear(sfb200_ar *h, int wid, int g, int l, const float *x, const float *bias, const float *residual, float *y,
+                  int M, int N, int K, int act, cudaStream_t s) {
+    if (M >= 9 && M <= 64 && h->wt)
+        return launch_linear_tc_ps(x, h->wt + wt_offset(&h->cfg, wid, g, l), bias, residual, y, M, N, K, act, s);
+    const float *W = W_(h, wid, g, l);
+    if (M >= 9) return launch_linear_tc(x, W, bias, residual, y, M, N, K, act, s);
     return launch_linear(x, W, bias, residual, y, M, N, K, act, s);
 }
 
@@ -244,14 +268,14 @@ static int block_prefill(sfb200_ar *h, int g, int l, float *x, int row0, int row
     const int d = h->cfg.n_embd, H = h->cfg.n_head, M = rows * T;
     float *ph = WS_<float>(h, h->buf.ph), *pqkv = WS_<float>(h, h->buf.pqkv), *pff = WS_<float>(h, h->buf.pff);
     SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN1_W, g, l), W_(h, SFB200_W_LN1_B, g, l), ph, M, d, s));
-    SFB_TRY(linear(h, ph, W_(h, SFB200_W_QKV_W, g, l), W_(h, SFB200_W_QKV_B, g, l), nullptr, pqkv, M, 3 * d, d, 0, s));
+    SFB_TRY(linear(h, SFB200_W_QKV_W, g, l, ph, W_(h, SFB200_W_QKV_B, g, l), nullptr, pqkv, M, 3 * d, d, 0, s));
     // with a rowmap the cache rows are rowmap[i] (cache base = row 0), otherwise rows row0 .. row0+rows-1
     SFB_TRY(launch_attn_prefill(pqkv, kcache(h, g, l, rowmap ? 0 : row0), vcache(h, g, l, rowmap ? 0 : row0), ph, rows, H, T,
                                 h->cfg.max_len, s, rowmap));
-    SFB_TRY(linear(h, ph, W_(h, SFB200_W_PROJ_W, g, l), W_(h, SFB200_W_PROJ_B, g, l), x, x, M, d, d, 0, s));
+    SFB_TRY(linear(h, SFB200_W_PROJ_W, g, l, ph, W_(h, SFB200_W_PROJ_B, g, l), x, x, M, d, d, 0, s));
     SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN2_W, g, l), W_(h, SFB200_W_LN2_B, g, l), ph, M, d, s));
-    SFB_TRY(linear(h, ph, W_(h, SFB200_W_FC1_W, g, l), W_(h, SFB200_W_FC1_B, g, l), nullptr, pff, M, 4 * d, d, 1, s));
-    SFB_TRY(linear(h, pff, W_(h, SFB200_W_FC2_W, g, l), W_(h, SFB200_W_FC2_B, g, l), x, x, M, d, 4 * d, 0, s));
+    SFB_TRY(linear(h, SFB200_W_FC1_W, g, l, ph, W_(h, SFB200_W_FC1_B, g, l), nullptr, pff, M, 4 * d, d, 1, s));
+    SFB_TRY(linear(h, SFB200_W_FC2_W, g, l, pff, W_(h, SFB200_W_FC2_B, g, l), x, x, M, d, 4 * d, 0, s));
     return SFB200_OK;
 }
 
@@ -262,7 +286,7 @@ static int block_step(sfb200_ar *h, int g, int l, float *x, cudaStream_t s) {
     float *hb = WS_<float>(h, h->buf.h), *qkv = WS_<float>(h, h->buf.qkv), *att = WS_<float>(h, h->buf.att);
     float *ff = WS_<float>(h, h->buf.ff), *part = WS_<float>(h, h->buf.part);
     SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN1_W, g, l), W_(h, SFB200_W_LN1_B, g, l), hb, B, d, s));
-    SFB_TRY(linear(h, hb, W_(h, SFB200_W_QKV_W, g, l), W_(h, SFB200_W_QKV_B, g, l), nullptr, qkv, B, 3 * d, d, 0, s));
+    SFB_TRY(linear(h, SFB200_W_QKV_W, g, l, hb, W_(h, SFB200_W_QKV_B, g, l), nullptr, qkv, B, 3 * d, d, 0, s));
     const bool timed = h->prof && !h->capturing;
     if (timed) {
         if (!h->ev) h->ev = new std::vector<cudaEvent_t>();
@@ -289,10 +313,10 @@ static int block_step(sfb200_ar *h, int g, int l, float *x, cudaStream_t s) {
         h->prof_bytes += key_rows * 2.0 * d * 4.0 + (double)B * 4.0 * d * 4.0;
         h->prof_bytes_per_row += (double)B * (2.0 * pos * d * 4.0 + 4.0 * d * 4.0);
     }
-    SFB_TRY(linear(h, att, W_(h, SFB200_W_PROJ_W, g, l), W_(h, SFB200_W_PROJ_B, g, l), x, x, B, d, d, 0, s));
+    SFB_TRY(linear(h, SFB200_W_PROJ_W, g, l, att, W_(h, SFB200_W_PROJ_B, g, l), x, x, B, d, d, 0, s));
     SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN2_W, g, l), W_(h, SFB200_W_LN2_B, g, l), hb, B, d, s));
-    SFB_TRY(linear(h, hb, W_(h, SFB200_W_FC1_W, g, l), W_(h, SFB200_W_FC1_B, g, l), nullptr, ff, B, 4 * d, d, 1, s));
-    SFB_TRY(linear(h, ff, W_(h, SFB200_W_FC2_W, g, l), W_(h, SFB200_W_FC2_B, g, l), x, x, B, d, 4 * d, 0, s));
+    SFB_TRY(linear(h, SFB200_W_FC1_W, g, l, hb, W_(h, SFB200_W_FC1_B, g, l), nullptr, ff, B, 4 * d, d, 1, s));
+    SFB_TRY(linear(h, SFB200_W_FC2_W, g, l, ff, W_(h, SFB200_W_FC2_B, g, l), x, x, B, d, 4 * d, 0, s));
     return SFB200_OK;
 }
 
@@ -300,7 +324,7 @@ static int head(sfb200_ar *h, int g, const float *x, float *logits, int rows, cu
     const int d = h->cfg.n_embd;
     float *hb = WS_<float>(h, h->buf.h);
     SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_HEAD_LN_W, g, 0), W_(h, SFB200_W_HEAD_LN_B, g, 0), hb, rows, d, s));
-    SFB_TRY(linear(h, hb, W_(h, SFB200_W_HEAD_W, g, 0), nullptr, nullptr, logits, rows, h->cfg.vocab[g], d, 0, s));
+    SFB_TRY(linear(h, SFB200_W_HEAD_W, g, 0, hb, nullptr, nullptr, logits, rows, h->cfg.vocab[g], d, 0, s));
     return SFB200_OK;
 }
 
@@ -483,5 +507,31 @@ extern "C" int sfb200_ar_profile_read(sfb200_ar *h, double *attn_ms, int64_t *at
     h->ev_used = 0;
     h->prof_bytes = 0.0;
     h->prof_bytes_per_row = 0.0;
+    return SFB200_OK;
+}
+
+extern "C" int64_t sfb200_ar_pretiled_floats(const sfb200_ar_config *cfg) {
+    Layout L;
+    if (make_layout(cfg, &L) != SFB200_OK) return -1;
+    const int d = cfg->n_embd;
+    return (int64_t)(cfg->n_layers[0] + cfg->n_layers[1]) * wt_block_floats(cfg) + tc_pretiled_floats(cfg->vocab[0], d) +
+           tc_pretiled_floats(cfg->vocab[1], d);
+}
+
+extern "C" int sfb200_ar_set_pretiled(sfb200_ar *h, float *pretiled, void *stream) {
+    if (!h || !pretiled) return SFB200_E_ARG;
+    cudaStream_t s = as_stream(stream);
+    const int d = h->cfg.n_embd;
+    h->wt = pretiled;
+    for (int g = 0; g < 2; ++g) {
+        for (int l = 0; l < h->cfg.n_layers[g]; ++l) {
+            SFB_TRY(launch_tc_pretile(W_(h, SFB200_W_QKV_W, g, l), h->wt + wt_offset(&h->cfg, SFB200_W_QKV_W, g, l), 3 * d, d, s));
+            SFB_TRY(launch_tc_pretile(W_(h, SFB200_W_PROJ_W, g, l), h->wt + wt_offset(&h->cfg, SFB200_W_PROJ_W, g, l), d, d, s));
+            SFB_TRY(launch_tc_pretile(W_(h, SFB200_W_FC1_W, g, l), h->wt + wt_offset(&h->cfg, SFB200_W_FC1_W, g, l), 4 * d, d, s));
+            SFB_TRY(launch_tc_pretile(W_(h, SFB200_W_FC2_W, g, l), h->wt + wt_offset(&h->cfg, SFB200_W_FC2_W, g, l), d, 4 * d, s));
+        }
+        SFB_TRY(launch_tc_pretile(W_(h, SFB200_W_HEAD_W, g, 0), h->wt + wt_offset(&h->cfg, SFB200_W_HEAD_W, g, 0), h->cfg.vocab[g], d, s));
+    }
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }   // the captured step used the other kernels
     return SFB200_OK;
 }

@@ -37,6 +37,11 @@ int launch_linear(const float *x, const float *W, const float *bias, const float
                   int act, cudaStream_t stream);
 int launch_linear_tc(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
                      int act, cudaStream_t stream);
+int64_t tc_pretiled_floats(int N, int K);
+int set_ps_timeline(unsigned long long *buf);
+int launch_tc_pretile(const float *W, float *Wt, int N, int K, cudaStream_t s);
+int launch_linear_tc_ps(const float *x, const float *Wt, const float *bias, const float *residual, float *y, int M, int N, int K,
+                        int act, cudaStream_t stream);
 int launch_attn_decode(const float *qkv, float *kc, float *vc, float *out, float *part, int B, int H, int max_len, int pos,
                        const int32_t *st, int n_split, cudaStream_t s, int group = 1, int lcond = 0, int lcond_delta = 0);
 int launch_attn_prefill(const float *qkv, float *kc, float *vc, float *out, int B, int H, int T, int max_len,

@@ -79,6 +79,17 @@ int sfb200_linear_tc(const float *x, const float *W, const float *bias, const fl
     if (!x || !W || !y || (act != 0 && act != 1)) return SFB200_E_ARG;
     return launch_linear_tc(x, W, bias, residual, y, M, N, K, act, as_stream(stream));
 }
+int64_t sfb200_tc_pretiled_floats(int N, int K) { return (N > 0 && K > 0 && K % 32 == 0) ? tc_pretiled_floats(N, K) : -1; }
+int sfb200_tc_pretile(const float *W, float *Wt, int N, int K, void *stream) {
+    if (!W || !Wt) return SFB200_E_ARG;
+    return launch_tc_pretile(W, Wt, N, K, as_stream(stream));
+}
+int sfb200_linear_tc_ps(const float *x, const float *Wt, const float *bias, const float *residual, float *y, int M, int N, int K,
+                        int act, void *stream) {
+    if (!x || !Wt || !y || (act != 0 && act != 1)) return SFB200_E_ARG;
+    return launch_linear_tc_ps(x, Wt, bias, residual, y, M, N, K, act, as_stream(stream));
+}
+int sfb200_debug_ps_timeline(void *buf16) { return set_ps_timeline(static_cast<unsigned long long *>(buf16)); }
 int sfb200_layernorm(const float *x, const float *w, const float *b, float *y, int rows, int d, void *stream) {
     if (!x || !w || !b || !y) return SFB200_E_ARG;
     return launch_layernorm(x, w, b, y, rows, d, as_stream(stream));

@@ -29,6 +29,19 @@ def linear_tc(x, W, bias=None, residual=None, act=None):
     return y
 
 
+def linear_tc_ps(x, W, bias=None, residual=None, act=None):
+    """linear() for M <= 64 rows from pre-split TF32 weight tiles (pretiles W on every call: test helper)."""
+    lib = _lib.load()
+    M, K = x.shape
+    N = W.shape[0]
+    wt = torch.empty(lib.sfb200_tc_pretiled_floats(N, K), dtype=torch.float32, device=x.device)
+    _lib.check(lib.sfb200_tc_pretile(_lib.ptr(W), _lib.ptr(wt), N, K, _lib.stream_ptr()), "sfb200_tc_pretile")
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    _lib.check(lib.sfb200_linear_tc_ps(_lib.ptr(x), _lib.ptr(wt), _lib.ptr(bias), _lib.ptr(residual), _lib.ptr(y), M, N, K,
+                                       1 if act == "gelu" else 0, _lib.stream_ptr()), "sfb200_linear_tc_ps")
+    return y
+
+
 def layernorm(x, w, b):
     lib = _lib.load()
     rows, d = x.shape

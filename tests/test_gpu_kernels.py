@@ -169,3 +169,24 @@ def test_linear_tc_deterministic_and_in_place(cuda):
     a = ops.linear_tc(x, W, b, residual=r)
     for _ in range(5):
         assert torch.equal(a, ops.linear_tc(x, W, b, residual=r))   # split-K partials are summed in split order
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 128, 64), (64, 1024, 1024), (16, 3072, 1024), (17, 4097, 1024), (33, 1024, 4096),
+                                   (64, 4096, 1024), (64, 4097, 1024), (9, 256, 128)])
+@pytest.mark.parametrize("mode", ["plain", "bias_gelu", "bias_res"])
+def test_linear_tc_presplit(cuda, M, N, K, mode):
+    """Decode-step GEMM from pre-split TF32 weight tiles (TMA bulk copies, both operands from shared memory)."""
+    x, W, b, r = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05), rnd(N, seed=3), rnd(M, N, seed=4)
+    xd, Wd = x.double(), W.double()
+    if mode == "plain":
+        ref = xd @ Wd.t()
+        out = ops.linear_tc_ps(x.to(cuda), W.to(cuda))
+    elif mode == "bias_gelu":
+        ref = F.gelu(xd @ Wd.t() + b.double())
+        out = ops.linear_tc_ps(x.to(cuda), W.to(cuda), b.to(cuda), act="gelu")
+    else:
+        ref = r.double() + xd @ Wd.t() + b.double()
+        out = ops.linear_tc_ps(x.to(cuda), W.to(cuda), b.to(cuda), residual=r.to(cuda))
+    err = (out.cpu().double() - ref).abs().max().item()
+    scale = max(1.0, ref.abs().max().item())
+    assert err < 2.5e-6 * scale * max(1.0, (K / 1024) ** 0.5), (err, scale)
