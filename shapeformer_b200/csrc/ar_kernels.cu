@@ -728,34 +728,98 @@ __global__ void __launch_bounds__(SMP_THREADS) ar_sample_kernel(SampleArgs a) {
     }
     __syncthreads();
 
-    // ---- bitonic sort, descending by (value, then lower index first)
-    for (int k = 2; k <= npad; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < (npad >> 1); i += SMP_THREADS) {
-                const int lo = i & (j - 1);
-                const int ia = ((i - lo) << 1) + lo, ib = ia + j;
-                const bool desc = (ia & k) == 0;
-                const unsigned long long ka = keys[ia], kb = keys[ib];
-                if ((ka < kb) == desc) { keys[ia] = kb; keys[ib] = ka; }
+    // ---- order the candidates, descending by (value, then lower index first), and apply top-k (ties at the k-th value are
+    //      kept — common.py:265-269).  Fast path for 0 < top_k <= 1024: an 8-bit radix select finds the k-th largest value,
+    //      the survivors are compacted and only they are sorted (1024-wide bitonic network instead of 8192-wide).
+    __shared__ int rsel[256];
+    __shared__ int sh_bin, sh_k, sh_cnt;
+    const int kk = min(top_k, V);
+    int np = npad;            // width of the sorted prefix array used below
+    int nkeep = V;
+    bool sorted = false;
+    if (kk > 0 && kk <= 1024) {
+        uint32_t prefix = 0, mask = 0;
+        int krem = kk;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            if (tid < 256) rsel[tid] = 0;
+            __syncthreads();
+            for (int v = tid; v < V; v += SMP_THREADS) {
+                const uint32_t o = (uint32_t)(keys[v] >> 32);
+                if ((o & mask) == prefix) atomicAdd(&rsel[(o >> shift) & 255u], 1);
             }
             __syncthreads();
+            if (tid == 0) {
+                int c = 0, b = 255;
+                for (; b > 0; --b) {
+                    if (c + rsel[b] >= krem) break;
+                    c += rsel[b];
+                }
+                sh_bin = b; sh_k = krem - c;
+            }
+            __syncthreads();
+            prefix |= (uint32_t)sh_bin << shift;
+            mask |= 0xFFu << shift;
+            krem = sh_k;
+        }
+        const uint32_t kth = prefix;                       // order key of the k-th largest value
+        unsigned long long *lst = reinterpret_cast<unsigned long long *>(ev);   // 1024 x u64 fits in the ev region
+        if (tid == 0) sh_cnt = 0;
+        lst[tid] = 0ull;                                   // SMP_THREADS == 1024
+        __syncthreads();
+        for (int v = tid; v < V; v += SMP_THREADS) {
+            const unsigned long long key = keys[v];
+            if ((uint32_t)(key >> 32) >= kth) {
+                const int pos = atomicAdd(&sh_cnt, 1);
+                if (pos < 1024) lst[pos] = key;
+            }
+        }
+        __syncthreads();
+        if (sh_cnt <= 1024) {
+            nkeep = sh_cnt;
+            for (int k = 2; k <= 1024; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    if (tid < 512) {
+                        const int lo = tid & (j - 1);
+                        const int ia = ((tid - lo) << 1) + lo, ib = ia + j;
+                        const bool desc = (ia & k) == 0;
+                        const unsigned long long ka = lst[ia], kb = lst[ib];
+                        if ((ka < kb) == desc) { lst[ia] = kb; lst[ib] = ka; }
+                    }
+                    __syncthreads();
+                }
+            }
+            keys[tid] = lst[tid];
+            __syncthreads();
+            np = 1024;
+            sorted = true;
         }
     }
-
-    // ---- top-k: keep everything >= the k-th largest (ties kept) — common.py:265-269
-    if (tid == 0) sh_nkeep = V;
-    __syncthreads();
-    const int kk = min(top_k, V);
-    if (kk > 0) {
-        const uint32_t kth = (uint32_t)(keys[kk - 1] >> 32);
-        for (int i = tid; i < V; i += SMP_THREADS) {
-            const uint32_t oi = (uint32_t)(keys[i] >> 32);
-            const uint32_t on = (i + 1 < V) ? (uint32_t)(keys[i + 1] >> 32) : 0u;
-            if (oi >= kth && (i + 1 == V || on < kth)) sh_nkeep = i + 1;
+    if (!sorted) {
+        for (int k = 2; k <= npad; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < (npad >> 1); i += SMP_THREADS) {
+                    const int lo = i & (j - 1);
+                    const int ia = ((i - lo) << 1) + lo, ib = ia + j;
+                    const bool desc = (ia & k) == 0;
+                    const unsigned long long ka = keys[ia], kb = keys[ib];
+                    if ((ka < kb) == desc) { keys[ia] = kb; keys[ib] = ka; }
+                }
+                __syncthreads();
+            }
         }
+        if (tid == 0) sh_nkeep = V;
+        __syncthreads();
+        if (kk > 0) {
+            const uint32_t kth = (uint32_t)(keys[kk - 1] >> 32);
+            for (int i = tid; i < V; i += SMP_THREADS) {
+                const uint32_t oi = (uint32_t)(keys[i] >> 32);
+                const uint32_t on = (i + 1 < V) ? (uint32_t)(keys[i + 1] >> 32) : 0u;
+                if (oi >= kth && (i + 1 == V || on < kth)) sh_nkeep = i + 1;
+            }
+        }
+        __syncthreads();
+        nkeep = sh_nkeep;
     }
-    __syncthreads();
-    const int nkeep = sh_nkeep;
 
     // ---- e_i = exp(l_i - l_0) for the kept prefix (softmax numerators in sorted order)
     auto sorted_val = [&](int i) -> float {
@@ -765,7 +829,7 @@ __global__ void __launch_bounds__(SMP_THREADS) ar_sample_kernel(SampleArgs a) {
     };
     const float l0 = sorted_val(0);
     float part = 0.f;
-    for (int i = tid; i < npad; i += SMP_THREADS) {
+    for (int i = tid; i < np; i += SMP_THREADS) {
         float e = 0.f;
         if (i < nkeep) e = expf(sorted_val(i) - l0);  // -inf -> 0
         ev[i] = e;
@@ -786,12 +850,12 @@ __global__ void __launch_bounds__(SMP_THREADS) ar_sample_kernel(SampleArgs a) {
     int n2 = nkeep;
     if (top_p > 0.0f) {
         const float sum1 = sh_sum;
-        const int per = npad / SMP_THREADS > 0 ? npad / SMP_THREADS : 1;
+        const int per = np / SMP_THREADS > 0 ? np / SMP_THREADS : 1;
         const int i0 = tid * per;
         double loc = 0.0;
         for (int u = 0; u < per; ++u) {
             const int i = i0 + u;
-            if (i < npad) loc += (double)(ev[i] / sum1);
+            if (i < np) loc += (double)(ev[i] / sum1);
         }
         // block exclusive scan of `loc`
         double inc = loc;
@@ -968,7 +1032,8 @@ int launch_sample(const SampleLaunch &p, cudaStream_t s) {
     a.mask_invalid_completion = p.sp.mask_invalid_completion;
     a.st = p.st; a.hist_row_stride = p.hist_row_stride; a.noise_step_stride = p.noise_step_stride;
     a.noise_row_stride = p.noise_row_stride > 0 ? p.noise_row_stride : p.V;
-    const size_t smem = (size_t)npad * 12;
+    // keys (8 B each) + the ev / compaction-list region (>= 1024 x 8 B)
+    const size_t smem = (size_t)npad * 8 + ((size_t)npad * 4 > 8192 ? (size_t)npad * 4 : 8192);
     static bool attr_done = false;
     if (!attr_done) {
         SFB_CUDA_TRY(cudaFuncSetAttribute(ar_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12));
