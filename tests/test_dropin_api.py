@@ -1,0 +1,82 @@
+"""CPU: the drop-in boundary — YAML `class:` plugin loading, constructor/state_dict compatibility with the reference, and the
+loud failure of the product path without a GPU (no CPU fallback)."""
+import os
+
+import pytest
+import torch
+
+from shapeformer_b200 import _lib, decoder, synth
+from shapeformer_b200.xgutils import optutil, sysutil
+from tests import refutil
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_yaml_plugin_builds_the_b200_classes():
+    opt = optutil.load_option(os.path.join(ROOT, "configs", "b200", "shapeformer_b200.yaml"))
+    model = sysutil.instantiate_from_opt(opt["pl_model_opt"])
+    assert type(model).__module__ == "shapeformer_b200.models.shapeformer.shapeformer"
+    assert model.transformer.get_block_size() == 812 and not model.transformer.training
+    assert model.representer.mask_invalid_completion is True and model.representer.max_length == 406
+    n = sum(p.numel() for p in model.transformer.parameters())
+    assert abs(n - 324.95e6) < 0.05e6
+    vq = model.representer.vqvae_model
+    assert type(vq).__name__ == "VQDIF" and sum(p.numel() for p in vq.decoder.parameters()) > 16e6
+    opt2 = optutil.load_option(os.path.join(ROOT, "configs", "b200", "vqdif_b200.yaml"))
+    assert type(sysutil.instantiate_from_opt(opt2["pl_model_opt"])).__name__ == "VQDIF"
+
+
+def test_inherit_from_merges_recursively(tmp_path):
+    (tmp_path / "base.yaml").write_text("a: {x: 1, y: {z: 2}}\nb: 3\n")
+    (tmp_path / "child.yaml").write_text("inherit_from: base.yaml\na: {y: {w: 5}}\n")
+    assert optutil.load_option(str(tmp_path / "child.yaml")) == {"a": {"x": 1, "y": {"z": 2, "w": 5}}, "b": 3}
+
+
+@pytest.mark.skipif(not refutil.have_reference(), reason="/root/reference not present")
+def test_state_dict_keys_match_the_reference():
+    from shapeformer_b200.models.shapeformer.transformer.mingpt import CondTupleGPT
+    from shapeformer_b200.models.vqdif.vqdif import VQDIF
+    cfg = synth.TINY_GPT
+    sd = synth.gpt_state_dict(cfg)
+    ref = refutil.ref_gpt(cfg, sd)
+    mine = CondTupleGPT(vocab_sizes=cfg["vocab_sizes"], extra_vocab_sizes=cfg["extra_vocab_sizes"],
+                        block_size=cfg["block_size"], tuple_n=2, n_layers=cfg["n_layers"], n_head=cfg["n_head"],
+                        n_embd=cfg["n_embd"])
+    want = {k: tuple(v.shape) for k, v in ref.state_dict().items() if not k.endswith("attn.mask")}
+    assert {k: tuple(v.shape) for k, v in mine.state_dict().items()} == want
+    mine.load_state_dict(ref.state_dict())                # reference checkpoints (with mask buffers) load strictly
+    vsd = synth.vqdif_state_dict()
+    dec, q = refutil.ref_vqdif_decoder(vsd)
+    opt = optutil.load_option(os.path.join(ROOT, "configs", "b200", "vqdif_b200.yaml"))
+    vq = sysutil.instantiate_from_opt(opt["pl_model_opt"])
+    ref_keys = {"decoder." + k: tuple(v.shape) for k, v in dec.state_dict().items()}
+    ref_keys.update({"quantizer." + k: tuple(v.shape) for k, v in q.state_dict().items()})
+    assert {k: tuple(v.shape) for k, v in vq.state_dict().items()} == ref_keys
+
+
+def test_product_path_fails_loudly_without_gpu():
+    from shapeformer_b200.models.shapeformer.transformer.mingpt import CondTupleGPT
+    cfg = synth.TINY_GPT
+    gpt = CondTupleGPT(vocab_sizes=cfg["vocab_sizes"], extra_vocab_sizes=cfg["extra_vocab_sizes"], block_size=64, tuple_n=2,
+                       n_layers=cfg["n_layers"], n_head=cfg["n_head"], n_embd=cfg["n_embd"])
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        gpt.packed_weights()
+    with pytest.raises(_lib.Sfb200Error):
+        decoder.ImplicitDecoder(synth.vqdif_state_dict(), "cpu")
+    with pytest.raises(NotImplementedError):
+        CondTupleGPT(vocab_sizes=(10, 10), extra_vocab_sizes=(10,), block_size=8, tuple_n=2, n_layers=(1, 1), n_head=3, n_embd=64)
+
+
+def test_tf32_split_and_fp32_conv_prologue_on_cpu():
+    """split_tf32: hi + lo reproduces the value to 2^-21 relative and both parts are TF32-representable; the fp32 mode of the
+    conv prologue is the oracle's op sequence."""
+    from oracle import sf_oracle as O
+    t = torch.randn(10000) * torch.logspace(-3, 3, 10000)
+    hi, lo = decoder.split_tf32(t)
+    assert ((hi.view(torch.int32) & 0x1FFF) == 0).all() and ((lo.view(torch.int32) & 0x1FFF) == 0).all()
+    assert ((hi + lo - t).abs() <= t.abs() * 2.0 ** -21).all()
+    sd = synth.vqdif_state_dict(seed=6)
+    x = O.get_code(sd, synth.code_grids(1, seed=1))
+    assert torch.equal(decoder.conv_prologue(sd, x, up_mode="fp32"), O.upsampler(sd, O.unet3d(sd, x)))
