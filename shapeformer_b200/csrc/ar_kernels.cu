@@ -141,8 +141,10 @@ __global__ void ar_take_last_kernel(const float *x, float *out, int d, int T, co
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// LayerNorm (eps 1e-5, biased variance), one warp per row.
+// LayerNorm (eps 1e-5, biased variance), one warp per row.  NV > 0: the row (NV float4 per lane, d = 128 NV) is read once
+// and kept in registers for the mean, the variance and the normalisation; NV == 0: generic three-pass form.
 // ---------------------------------------------------------------------------------------------------------------------
+template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float *x, const float *__restrict__ w,
                                                         const float *__restrict__ bvec, float *y, int rows,
                                                         int d) {
@@ -152,6 +154,35 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *x, const fl
     if (warp >= rows) return;
     const float *xr = x + (size_t)warp * d;
     float *yr = y + (size_t)warp * d;
+    if (NV > 0) {
+        float4 v[NV > 0 ? NV : 1];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            v[j] = ld4(xr + lane * 4 + 128 * j);
+            s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+        }
+        const float mean = warp_sum(s) / (float)d;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, e = v[j].w - mean;
+            q += (a * a + b * b) + (c * c + e * e);
+        }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)d + 1e-5f);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int i = lane * 4 + 128 * j;
+            const float4 g = ld4(w + i), bb = ld4(bvec + i);
+            float4 r;
+            r.x = (v[j].x - mean) * rstd * g.x + bb.x;
+            r.y = (v[j].y - mean) * rstd * g.y + bb.y;
+            r.z = (v[j].z - mean) * rstd * g.z + bb.z;
+            r.w = (v[j].w - mean) * rstd * g.w + bb.w;
+            st4(yr + i, r);
+        }
+        return;
+    }
     float s = 0.f;
     for (int i = lane * 4; i < d; i += 128) {
         float4 v = ld4(xr + i);
@@ -994,7 +1025,10 @@ int launch_take_last(const float *x, float *out, int B, int d, int T, cudaStream
 int launch_layernorm(const float *x, const float *w, const float *b, float *y, int rows, int d, cudaStream_t s) {
     if (rows <= 0) return SFB200_OK;
     if (d % 4 != 0) return SFB200_E_ARG;
-    return launch_ex("layernorm", layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, dim3(1, 1, 1), x, w, b, y, rows, d);
+    const dim3 grid((rows + 7) / 8);
+    if (d == 1024) return launch_ex("layernorm", layernorm_kernel<8>, grid, dim3(256), 0, s, dim3(1, 1, 1), x, w, b, y, rows, d);
+    if (d == 128) return launch_ex("layernorm", layernorm_kernel<1>, grid, dim3(256), 0, s, dim3(1, 1, 1), x, w, b, y, rows, d);
+    return launch_ex("layernorm", layernorm_kernel<0>, grid, dim3(256), 0, s, dim3(1, 1, 1), x, w, b, y, rows, d);
 }
 int launch_attn_decode(const float *qkv, float *kc, float *vc, float *out, float *part, int B, int H, int max_len, int pos,
                        const int32_t *st, int n_split, cudaStream_t s, int group, int lcond, int lcond_delta) {
