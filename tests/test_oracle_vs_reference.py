@@ -142,3 +142,24 @@ def test_tokens_to_dense_matches_reference():
     r = m["common"].batch_sparse2dense(packed, 123, 16, return_flattened=False, dim=3)[0]
     o = O.tokens_to_dense(toks, 123)
     assert torch.equal(r, o)
+
+
+def test_sample_indices_edge_cases_match_reference():
+    """Unconditional start (L_cond = 1, the reference's `uncond` conditioning = one end tuple), early termination with the
+    masks on, and a temperature != 1."""
+    cfg = synth.TINY_GPT
+    sd = synth.gpt_state_dict(cfg, seed=9, peaky=True)
+    spec = O.GPTSpec(**cfg)
+    for masks, Lc, steps, T in (((True, False), 1, 10, 1.0), ((True, True), 5, 30, 0.8), ((False, False), 2, 6, 1.5)):
+        sf = refutil.ref_shapeformer(cfg, sd, mask_invalid=masks[0], mask_invalid_completion=masks[1])
+        c = torch.tensor([[list(END)]]).repeat(3, 1, 1) if Lc == 1 else synth.cond_indices(3, Lc, seed=Lc)
+        torch.manual_seed(3)
+        rx, rh = sf.sample_indices(c_indices=c, z_indices=c[:, :0], max_steps=steps, best_in_first=True, top_k=25, top_p=0.6,
+                                   temperature=T)
+        torch.manual_seed(3)
+        ox, oh = O.sample_indices(sd, spec, c, c[:, :0], steps, END, True, 25, 0.6, T, masks[0], masks[1], cached=True)
+        assert torch.equal(rx, ox), (masks, Lc)
+        assert rx.shape[1] <= steps
+        for a, b in zip(rh, oh):
+            fin = torch.isfinite(a)
+            assert torch.equal(fin, torch.isfinite(b)) and (a[fin] - b[fin]).abs().max() < 3e-5
