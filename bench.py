@@ -22,9 +22,14 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# keep stdout to the single JSON line the driver parses: NCCL prints its version banner there when NCCL_DEBUG=VERSION/INFO
-if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("SFB200_KEEP_NCCL_DEBUG"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# Keep stdout to the single JSON line the driver parses: C libraries (NCCL prints "NCCL version ..." on fd 1) and stray
+# prints are diverted to stderr by pointing fd 1 at fd 2; the JSON line is written to the saved original stdout at the end.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
 
 import torch  # noqa: E402
 
@@ -212,7 +217,7 @@ def main():
                 vals.append(r["value"]); secs.append(r["sample_seconds"])
         v = statistics.mean(vals)
         r["value"] = v
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "shapes/s", "n_gpus": args.gpus,
+        emit(({"impl": "reference", "metric": METRIC, "value": v, "unit": "shapes/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(secs),
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                           "data": "synthetic", "config": workload, "cpu_baseline": r,
@@ -384,7 +389,7 @@ def main():
                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload, "clocks": clk,
                "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
                "stepping": "cuda graph replay of one AR step" if use_graph else "eager launches"}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
