@@ -50,7 +50,7 @@ int sfb200_code_gather(const int64_t *code_ind, const float *codebook, float *ou
 int sfb200_grid_to_channels_last(const float *src, float *dst, int B, int C, int64_t S, void *stream);
 
 /* Number of floats of the packed LocalDecoder MLP weights (hidden = c_dim = 32, n_blocks = 5): see
- * shapeformer_b200/models/vqdif/dec.py::pack_mlp_weights for the order. */
+ * shapeformer_b200/decoder.py::pack_mlp_weights for the order. */
 #define SFB200_DEC_HIDDEN 32
 #define SFB200_DEC_BLOCKS 5
 #define SFB200_DEC_MLP_FLOATS (32 * 3 + 32 + 5 * (3 * (32 * 32 + 32)) + 32 + 1)
@@ -64,7 +64,7 @@ int sfb200_decoder_set_weights(const float *mlp_weights, void *stream);
  *   grid   (B, R, R, R, 32) fp32 channel-last feature grid (output of UNet3D+Upsampler),
  *   xtg    (B or 1, N, 3) fp32 query points in [-1,1]; xtg_batch_stride = N*3 or 0 when shared by all shapes,
  *   logits (B, N) fp32 occupancy logits (the reference's (B,N,1)).
- * impl: 0 = default (tcgen05 split-bf16 tensor-core kernel), 1 = fp32 FFMA kernel (verification / small N).
+ * impl: 0 = default (tcgen05 kernel, TF32 hi/lo operand split, 3 MMAs per product), 1 = fp32 FFMA kernel (cross-check).
  * sigmoid != 0 writes occupancy = 1/(1+exp(-logit)) instead (decode_sample_indices, shapeformer/shapeformer.py:388). */
 int sfb200_decoder_points(const float *grid, const float *xtg, int64_t xtg_batch_stride, float *logits, int B, int R,
                           int64_t N, int impl, int sigmoid, void *stream);
