@@ -51,8 +51,15 @@ def parse():
     ap.add_argument("--top-k", type=int, default=50)
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"])
     ap.add_argument("--tiny", action="store_true", help="tiny transformer (smoke runs; NOT a valid bench number)")
+    ap.add_argument("--top-p", type=float, default=0.0)
+    ap.add_argument("--mode", default="weak", choices=["weak", "strong"],
+                    help="weak: --rows per GPU (default); strong: --rows in total, split over the ranks in blocks of sample_n "
+                         "(BASELINE cfg 4 as written: 64 rows over 2/4 GPUs)")
+    ap.add_argument("--cfg2", action="store_true",
+                    help="BASELINE cfg 2: one row, greedy (top_k 1, top_p 0.001), no best_in_first (single-shape latency)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the eager attention-profiling pass and the decoder timing")
     return ap.parse_args()
 
 
@@ -90,100 +97,127 @@ class ClockSampler:
 
 
 def measured_peaks():
+    """Roofline denominators: the driver-written measurement on this pool's B200s, else the profiling guide's fallback."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
             j = json.load(open(p))
-            return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            return {"hbm_gbs": float(j["hbm_gbs"]), "bf16_tflops": float(j["bf16_tflops"]),
+                    "bf16_tflops_sustained": float(j.get("bf16_tflops_sustained", j["bf16_tflops"])),
+                    "source": "measured (MEASURED_PEAKS.json)"}
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-def ncu_traffic(alg_bytes_per_launch):
-    """Per-launch DRAM bytes of the attention kernel: the committed `ncu --set full` capture measured
-    dram__bytes_read+write at one context length; its ratio to the algorithmic bytes (1.03: no re-reads) is applied to this
-    run's average algorithmic bytes per launch."""
-    p = os.path.join(ROOT, "profiles", "attn_decode_ncu.json")
+def ncu_capture(name):
+    """Summary of the committed `ncu --set full` capture of a kernel (profiles/r2_ncu_<name>.json, written by
+    scripts/ncu_summary.py from the .ncu-rep of the same bench command) or None."""
+    p = os.path.join(ROOT, "profiles", f"r2_ncu_{name}.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p))["traffic_over_algorithmic"] * alg_bytes_per_launch
+            return json.load(open(p))
         except Exception:
             pass
     return None
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def pick_cpu_threads(gpt_sd, cfg):
-    """torch's CPU kernels do not scale to every core of a big host (128 threads were 20x slower than 8 on the bench box):
-    time one transformer block of the reference algorithm at L = 256 for several thread counts and keep the fastest."""
-    from oracle import sf_oracle as O
-    n = os.cpu_count() or 1
-    x = torch.randn(1, 256, cfg["n_embd"])
-    best, best_t = 1, float("inf")
-    for t in sorted({c for c in (4, 8, 16, 32, 64, n) if c <= n}):
-        torch.set_num_threads(t)
-        with torch.no_grad():
-            O.gpt_block(gpt_sd, "blocks.0.0.", x, cfg["n_head"])
-            t0 = time.perf_counter()
-            for _ in range(3):
-                O.gpt_block(gpt_sd, "blocks.0.0.", x, cfg["n_head"])
-            dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = t, dt
-    torch.set_num_threads(best)
-    return best
+CPU_THREADS = 32   # fixed: torch's CPU kernels do not scale past ~32 threads on the bench hosts (128 threads measured 3x
+                   # slower); a per-run calibration made the CPU arm vary 4x between runs in round 1
 
 
-def cpu_reference_sample(args, gpt_sd, vq_sd, cfg, threads):
-    """The reference algorithm on the host cores (oracle port, faithful = UNCACHED like the reference): time one row's AR
-    step at three context lengths and one 64^3 decode, then integrate over the 512-step schedule.  Returns a dict."""
-    from oracle import sf_oracle as O
-    torch.set_num_threads(threads)
-    spec = O.GPTSpec(**cfg)
-    from shapeformer_b200 import synth
-    Lc, S = args.lcond, args.ar_steps
-    lens = sorted({Lc, Lc + S // 2, Lc + S - 1})
-    t_at = {}
-    g = torch.Generator().manual_seed(0)
-    for L in lens:
-        c = synth.cond_indices(1, Lc, seed=1)
-        z = torch.stack([torch.sort(torch.randperm(4096, generator=g)[:L - Lc])[0],
-                         torch.randint(0, 4096, (L - Lc,), generator=g)], -1)[None]
-        idx = torch.cat([c, z], 1)
-        extra = O.extra_indices(c, z, END[0])
-        t0 = time.perf_counter()
+class CpuArm:
+    """The reference's own CPU path for one row of the workload, timed as a bounded sample: one UNCACHED AR step (the
+    reference recomputes the whole prefix every step, shapeformer.py:72-89) at three context lengths + one 64^3 decode,
+    integrated over the step schedule.  kind "reference": the unmodified reference modules (oracle/_ref or /root/reference
+    through oracle/ref_shim.py); kind "port": oracle/sf_oracle.py when the reference tree is not importable."""
+
+    def __init__(self, args, gpt_sd, vq_sd, cfg):
+        from oracle import ref_models
+        from shapeformer_b200 import synth
+        self.args, self.cfg = args, cfg
+        self.threads = min(CPU_THREADS, os.cpu_count() or 1)
+        torch.set_num_threads(self.threads)
+        Lc, S = args.lcond, args.ar_steps
+        self.lens = sorted({Lc, Lc + S // 2, Lc + S - 1})
+        g = torch.Generator().manual_seed(0)
+        self.c = synth.cond_indices(1, Lc, seed=1)
+        self.z = {L: torch.stack([torch.sort(torch.randperm(4096, generator=g)[:L - Lc])[0],
+                                  torch.randint(0, 4096, (L - Lc,), generator=g)], -1)[None] for L in self.lens}
+        self.code = synth.code_grids(1, seed=2)
+        self.Xtg = synth.make_grid(args.grid)[None]
+        self.kind = "reference" if ref_models.have_reference() else "port"
+        if self.kind == "reference":
+            self.sf = ref_models.ref_shapeformer(cfg, gpt_sd, mask_invalid=False, mask_invalid_completion=False)
+            self.dec, self.q = ref_models.ref_vqdif_decoder(vq_sd)
+        else:
+            self.gpt_sd, self.vq_sd = gpt_sd, vq_sd
+        self.t_at = {L: [] for L in self.lens}
+        self.t_dec = []
+
+    def _ar_step(self, L):
+        a = self.args
+        if self.kind == "reference":
+            self.sf.sample_indices(c_indices=self.c, z_indices=self.z[L], max_steps=1, best_in_first=not a.cfg2,
+                                   top_k=a.top_k, top_p=a.top_p, temperature=1.0)
+            return
+        from oracle import sf_oracle as O
+        spec, sd, Lc = O.GPTSpec(**self.cfg), self.gpt_sd, a.lcond
+        idx = torch.cat([self.c, self.z[L]], 1)
+        extra = O.extra_indices(self.c, self.z[L], END[0])
+        x = O.gpt_embed(sd, idx, extra, Lc)
+        x = O.gpt_group(sd, spec, 0, x)
+        l0 = O.gpt_head(sd, 0, x)[:, -1]
+        l0 = O.sampling_masker(l0, torch.cat([idx, idx[:, -1:]], 1), Lc, L - Lc, 0, END, False, False)
+        q = torch.empty(1, 4097).exponential_(1.0)
+        O.sample_rows(l0, q, a.top_k, a.top_p, 1.0); O.sample_rows(l0, q, 1, 0.001, 1.0)
+        x = x + sd["tok_embs.0.weight"][idx[:, :, 0]]
+        x = O.gpt_group(sd, spec, 1, x)
+        l1 = O.gpt_head(sd, 1, x)[:, -1]
+        O.sample_rows(l1, q, a.top_k, a.top_p, 1.0); O.sample_rows(l1, q, 1, 0.001, 1.0)
+
+    def _decode(self):
+        if self.kind == "reference":
+            from oracle import ref_models
+            ref_models.ref_decode_index(self.dec, self.q, self.code, self.Xtg)
+        else:
+            from oracle import sf_oracle as O
+            O.decode_index(self.vq_sd, self.code, self.Xtg)
+
+    def sample_once(self):
+        """One bounded sample: an AR step at each context length + one decode.  Returns its wall seconds."""
+        torch.set_num_threads(self.threads)
+        tot = 0.0
         with torch.no_grad():
-            x = O.gpt_embed(gpt_sd, idx, extra, Lc)
-            x = O.gpt_group(gpt_sd, spec, 0, x)
-            l0 = O.gpt_head(gpt_sd, 0, x)[:, -1]
-            l0 = O.sampling_masker(l0, torch.cat([idx, idx[:, -1:]], 1), Lc, L - Lc, 0, END, False, False)
-            q = torch.empty(1, 4097).exponential_(1.0)
-            O.sample_rows(l0, q, args.top_k, 0.0, 1.0); O.sample_rows(l0, q, 1, 0.001, 1.0)
-            x = x + gpt_sd["tok_embs.0.weight"][idx[:, :, 0]]
-            x = O.gpt_group(gpt_sd, spec, 1, x)
-            l1 = O.gpt_head(gpt_sd, 1, x)[:, -1]
-            O.sample_rows(l1, q, args.top_k, 0.0, 1.0); O.sample_rows(l1, q, 1, 0.001, 1.0)
-        t_at[L] = time.perf_counter() - t0
-    # piecewise-linear integral of t(L) over L = Lc .. Lc+S-1
-    ar = 0.0
-    for j in range(S):
-        L = Lc + j
-        lo = max(l for l in lens if l <= L)
-        hi = min(l for l in lens if l >= L)
-        ar += t_at[lo] if hi == lo else t_at[lo] + (t_at[hi] - t_at[lo]) * (L - lo) / (hi - lo)
-    code = synth.code_grids(1, seed=2)
-    Xtg = synth.make_grid(args.grid)[None]
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        O.decode_index(vq_sd, code, Xtg)
-    dec = time.perf_counter() - t0
-    per_row = ar + dec
-    return {"value": 1.0 / per_row, "unit": "shapes/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
-            "sample": (f"oracle port of the reference (uncached full forward per step, torch CPU fp32), 1 row: AR steps timed "
-                       f"at L={lens} ({', '.join(f'{t_at[l]:.2f}s' for l in lens)}) integrated over {S} steps = {ar:.0f}s, "
-                       f"+ one {args.grid}^3 decode = {dec:.2f}s; cost is linear in rows"),
-            "sample_seconds": sum(t_at.values()) + dec}
+            for L in self.lens:
+                t0 = time.perf_counter(); self._ar_step(L); dt = time.perf_counter() - t0
+                self.t_at[L].append(dt); tot += dt
+            t0 = time.perf_counter(); self._decode(); dt = time.perf_counter() - t0
+            self.t_dec.append(dt); tot += dt
+        return tot
+
+    def result(self, skip=0):
+        """shapes/s from the per-point MINIMUM over the repeats (after `skip` warm-up samples); spread = max/min."""
+        S, Lc = self.args.ar_steps, self.args.lcond
+        t = {L: min(v[skip:]) for L, v in self.t_at.items()}
+        dec = min(self.t_dec[skip:])
+        ar = 0.0
+        for j in range(S):   # piecewise-linear integral of t(L) over L = Lc .. Lc+S-1
+            L = Lc + j
+            lo = max(l for l in self.lens if l <= L)
+            hi = min(l for l in self.lens if l >= L)
+            ar += t[lo] if hi == lo else t[lo] + (t[hi] - t[lo]) * (L - lo) / (hi - lo)
+        spread = max(max(v[skip:]) / min(v[skip:]) for v in list(self.t_at.values()) + [self.t_dec])
+        n = len(self.t_dec) - skip
+        what = ("the UNMODIFIED reference (ShapeFormer.sample_indices + LocalDecoder, via oracle/ref_shim.py)"
+                if self.kind == "reference" else "oracle port of the reference (uncached full forward per step)")
+        return {"value": 1.0 / (ar + dec), "unit": "shapes/s", "cores": self.threads, "host_cores": os.cpu_count(),
+                "kind": self.kind, "repeats": n, "spread_max_over_min": spread,
+                "sample": (f"{what}, torch CPU fp32, {self.threads} threads (fixed), 1 row: one AR step at L={self.lens} "
+                           f"(min of {n}: {', '.join(f'{t[l]:.2f}s' for l in self.lens)}) integrated over {S} steps = "
+                           f"{ar:.0f}s, + one {self.args.grid}^3 decode = {dec:.2f}s; cost is linear in rows"),
+                "sample_seconds": sum(t.values()) + dec}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -193,35 +227,46 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     from shapeformer_b200 import synth
+    from shapeformer_b200 import dist as sdist
     cfg = synth.TINY_GPT if args.tiny else synth.SHIPPED_GPT
     if args.tiny:
         cfg = dict(cfg, block_size=812)
-    workload = {"workload": (f"cfg4/5-style completion batch per GPU: {args.rows} rows ({args.rows // args.sample_n} shapes x "
-                             f"sample_n {args.sample_n}), L_cond {args.lcond}, {args.ar_steps} AR steps fixed-length "
-                             f"(masks off), top_k {args.top_k}, top_p 0, T 1, best_in_first, + {args.grid}^3 decode"),
-                "rows_per_gpu": args.rows, "l_cond": args.lcond, "ar_steps": args.ar_steps, "grid": args.grid,
-                "transformer": "tiny (INVALID as a bench number)" if args.tiny else "shipped 20+4 x 1024 (325M)",
-                "weights": "synthetic seed 314 (reference init)", "parallelism": f"rows sharded x{world}",
-                "l2_policy": "inputs larger than L2 (KV cache 9.7 GB, feature grids 2.1 GB per batch)"}
+    if args.cfg2:
+        args.rows, args.sample_n, args.top_k, args.top_p = 1, 1, 1, 0.001
+    best_first = not args.cfg2
+    # rows of this rank: weak = --rows each; strong = --rows in total, contiguous blocks of whole shapes (dist.row_block)
+    if args.mode == "strong":
+        lo, hi = sdist.row_block(args.rows, rank, world, group=args.sample_n)
+        B, rows_total = hi - lo, args.rows
+        split = [sdist.row_block(args.rows, r, world, group=args.sample_n) for r in range(world)]
+        per_gpu = "/".join(str(b - a) for a, b in split)
+    else:
+        B, rows_total, per_gpu = args.rows, args.rows * world, str(args.rows)
+    what = ("cfg 2: single-shape latency, greedy" if args.cfg2 else
+            "cfg 4 as written (rows sharded over the GPUs)" if args.mode == "strong" else "cfg4/5-style completion batch per GPU")
+    workload = {"workload": (f"{what}: {per_gpu} rows per GPU ({rows_total // args.sample_n} shapes x sample_n "
+                             f"{args.sample_n} in total), L_cond {args.lcond}, {args.ar_steps} AR steps fixed-length "
+                             f"(masks off), top_k {args.top_k}, top_p {args.top_p:g}, T 1"
+                             f"{', best_in_first' if best_first else ''}, + {args.grid}^3 decode"),
+                "rows_per_gpu": per_gpu, "rows_total": rows_total, "l_cond": args.lcond, "ar_steps": args.ar_steps,
+                "grid": args.grid, "transformer": "tiny (INVALID as a bench number)" if args.tiny else "shipped 20+4 x 1024 (325M)",
+                "weights": "synthetic seed 314 (reference init)", "parallelism": f"rows sharded x{world} ({args.mode})",
+                "l2_policy": "inputs larger than L2 (KV cache 9.7 GB, feature grids 2.1 GB per 64-row batch)"}
+    scaling = "strong" if args.mode == "strong" else "weak"
 
     if args.impl == "reference":
         if rank != 0:
             return
         gpt_sd = synth.gpt_state_dict(cfg, seed=314, peaky=False)
         vq_sd = synth.vqdif_state_dict(seed=314)
-        threads = pick_cpu_threads(gpt_sd, cfg)
-        vals, secs = [], []
-        for i in range(args.warmup + args.steps):
-            r = cpu_reference_sample(args, gpt_sd, vq_sd, cfg, threads)
-            if i >= args.warmup:
-                vals.append(r["value"]); secs.append(r["sample_seconds"])
-        v = statistics.mean(vals)
-        r["value"] = v
-        emit(({"impl": "reference", "metric": METRIC, "value": v, "unit": "shapes/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(secs),
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                          "data": "synthetic", "config": workload, "cpu_baseline": r,
-                          "e2e": {"value": v, "unit": "shapes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        arm = CpuArm(args, gpt_sd, vq_sd, cfg)
+        secs = [arm.sample_once() for _ in range(args.warmup + args.steps)]
+        r = arm.result(skip=args.warmup)
+        emit({"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "shapes/s", "n_gpus": args.gpus,
+              "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(secs[args.warmup:]),
+              "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+              "config": workload, "cpu_baseline": r,
+              "e2e": {"value": r["value"], "unit": "shapes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
@@ -232,7 +277,7 @@ def main():
     import torch.distributed as dist
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from shapeformer_b200 import _lib, ar, decoder
+    from shapeformer_b200 import _lib
     from shapeformer_b200.models.shapeformer.shapeformer import ShapeFormer
     from shapeformer_b200.models.vqdif.vqdif import VQDIF
     lib = _lib.load()
@@ -260,12 +305,11 @@ def main():
         model.transformer.load_state_dict(gpt_sd)
         vq.load_state_dict(vq_sd, strict=False)
     model.to(dev); vq.to(dev)
-    from shapeformer_b200 import dist as sdist
     sdist.broadcast_parameters([p.data for p in list(model.transformer.parameters()) + list(vq.parameters())], src=0)
     model.representer.vqvae_model = vq
     model.history_device = None     # value arm: history stays off; the e2e arm turns the reference's CPU history on
 
-    B, Lc, S, R = args.rows, args.lcond, args.ar_steps, args.grid
+    Lc, S, R = args.lcond, args.ar_steps, args.grid
     # distinct conditioning per shape, repeated sample_n times (shapeformer.py:229), different per rank
     c_host = synth.cond_indices(B // args.sample_n, Lc, seed=1000 + rank).repeat_interleave(args.sample_n, 0).pin_memory()
     c_dev = c_host.to(dev)
@@ -275,20 +319,19 @@ def main():
     eng = vq.engine()
     use_graph = {"auto": True, "on": True, "off": False}[args.graph]
     sampler = model.transformer.sampler(B, Lc, S, END, keep_history=False)
-    gather_tok = [torch.empty(B, S, 2, dtype=torch.int64, device=dev) for _ in range(world)] if world > 1 else None
-    gather_occ = [torch.empty(B, R ** 3, dtype=torch.float32, device=dev) for _ in range(world)] if world > 1 else None
+    skw = dict(top_k=args.top_k, top_p=args.top_p, temperature=1.0, best_in_first=best_first, mask_invalid=False,
+               mask_invalid_completion=False, stop_early=False)
 
     def step_value():
-        x, _ = sampler.sample(c_dev, S, top_k=args.top_k, top_p=0.0, temperature=1.0, best_in_first=True,
-                              mask_invalid=False, mask_invalid_completion=False, use_graph=use_graph, stop_early=False)
+        x, _ = sampler.sample(c_dev, S, use_graph=use_graph, **skw)
         dense = eng.tokens_to_dense(x, empty)
         occ = eng.occupancy(dense, xtg_dev)
-        if world > 1:
-            dist.all_gather(gather_tok, x.contiguous())
-            dist.all_gather(gather_occ, occ)
+        if world > 1:      # ONE all-gather of the per-row outputs per batch (row blocks may be unequal in strong mode)
+            sdist.gather_rows(x.contiguous())
+            sdist.gather_rows(occ)
         return x, occ
 
-    def timed(fn, n):
+    def timed(fn, n, per_rank=False):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -298,11 +341,17 @@ def main():
             fn()
         e1.record()
         torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        mine = e0.elapsed_time(e1)
+        ms = torch.tensor([mine], device=dev)
+        each = None
         if world > 1:
+            if per_rank:
+                each = [torch.empty_like(ms) for _ in range(world)]
+                dist.all_gather(each, ms)
+                each = [float(e) / n for e in each]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             dist.barrier()
-        return float(ms)
+        return float(ms), each
 
     for _ in range(args.warmup):
         step_value()
@@ -310,43 +359,82 @@ def main():
     clocks = ClockSampler(local)
     clocks.start()
     l0 = lib.sfb200_launch_count()
-    ms = timed(step_value, args.steps)
+    ms, per_rank_ms = timed(step_value, args.steps, per_rank=True)
     launches = lib.sfb200_launch_count() - l0
     clk = clocks.stop()
-
-    # ---- roofline of the dominant kernel (single-query attention + KV append): one more pass over the SAME batch with eager
-    #      launches so that every attention launch can be bracketed by CUDA events on the launching stream
-    import ctypes
-    roof = None
-    _lib.check(lib.sfb200_ar_profile(sampler.handle, 1))
-    torch.cuda.synchronize()
-    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pe0.record()
-    sampler.sample(c_dev, S, top_k=args.top_k, top_p=0.0, temperature=1.0, best_in_first=True, mask_invalid=False,
-                   mask_invalid_completion=False, use_graph=False, stop_early=False)
-    pe1.record()
-    torch.cuda.synchronize()
-    a_ms, a_n, a_b, a_br = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double(), ctypes.c_double()
-    _lib.check(lib.sfb200_ar_profile_read(sampler.handle, ctypes.byref(a_ms), ctypes.byref(a_n), ctypes.byref(a_b),
-                                          ctypes.byref(a_br)))
-    _lib.check(lib.sfb200_ar_profile(sampler.handle, 0))
-    peak, how = measured_peaks()
-    if a_n.value:
-        ach = a_b.value / (a_ms.value * 1e-3) / 1e9
-        roof = {"kernel": "attn_decode_kernel (single-query attention + KV append)", "bound": "hbm", "achieved": ach,
-                "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic(a_b.value / a_n.value),
-                "peak_source": how + "; sustained-style figure (kernel timed inside a long step)",
-                "launches": a_n.value, "avg_launch_us": 1e3 * a_ms.value / a_n.value,
-                "algorithmic_bytes_per_launch": a_b.value / a_n.value,
-                "per_row_formula_bytes_per_launch": a_br.value / a_n.value,
-                "per_row_formula_gbs": a_br.value / (a_ms.value * 1e-3) / 1e9,
-                "note": "achieved = bytes that must move / time: the conditioning-prefix K/V of the sample_n rows of a shape is "
-                        "read once per shape (SURVEY §7 item 5); per_row_formula_* applies SURVEY §8d's per-row byte count",
-                "share_of_ar_pass": a_ms.value / pe0.elapsed_time(pe1),
-                "how": "CUDA events around every attention launch of one eager AR pass over the same batch, right after the "
-                       "timed region (the timed region replays the step as a CUDA graph, where events cannot be read)"}
-    rows_total = B * world
     value = rows_total * args.steps / (ms * 1e-3)
+
+    def ev_time(fn, reps=3):
+        """min over `reps` of the CUDA-event time of fn() on the current stream (ms)."""
+        best = float("inf")
+        out = None
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); out = fn(); b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return best, out
+
+    # ---- rooflines (after the timed region, same batch).  (1) attention = the dominant kernel: one more AR pass with eager
+    #      launches so that every attention launch can be bracketed by CUDA events on the launching stream; (2) the implicit
+    #      decoder's point kernel timed alone (events) against the TF32 tensor peak.
+    import ctypes
+    roof = roof_dec = breakdown = None
+    if not args.no_roofline:
+        _lib.check(lib.sfb200_ar_profile(sampler.handle, 1))
+        torch.cuda.synchronize()
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        sampler.sample(c_dev, S, use_graph=False, **skw)
+        pe1.record()
+        torch.cuda.synchronize()
+        a_ms, a_n, a_b, a_br = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double(), ctypes.c_double()
+        _lib.check(lib.sfb200_ar_profile_read(sampler.handle, ctypes.byref(a_ms), ctypes.byref(a_n), ctypes.byref(a_b),
+                                              ctypes.byref(a_br)))
+        _lib.check(lib.sfb200_ar_profile(sampler.handle, 0))
+        peaks = measured_peaks()
+        if a_n.value:
+            ach = a_b.value / (a_ms.value * 1e-3) / 1e9
+            ncu = ncu_capture("attn_decode")
+            roof = {"kernel": "attn_decode_kernel (single-query attention + KV append)", "bound": "hbm", "achieved": ach,
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                    "traffic": ncu.get("dram_bytes_per_launch") if ncu else None,
+                    "traffic_note": (f"ncu --set full capture of this kernel at position {ncu.get('position')} of the same batch: "
+                                     f"dram read+write {ncu.get('dram_bytes_per_launch'):.4g} B vs algorithmic "
+                                     f"{ncu.get('algorithmic_bytes'):.4g} B at that position "
+                                     f"(x{ncu.get('dram_bytes_per_launch') / ncu.get('algorithmic_bytes'):.2f}), "
+                                     f"{ncu.get('duration_us'):.1f} us under ncu") if ncu else None,
+                    "peak_source": peaks["source"] + " hbm_gbs (copy bandwidth)",
+                    "launches": a_n.value, "avg_launch_us": 1e3 * a_ms.value / a_n.value,
+                    "algorithmic_bytes_per_launch": a_b.value / a_n.value,
+                    "per_row_formula_bytes_per_launch": a_br.value / a_n.value,
+                    "per_row_formula_gbs": a_br.value / (a_ms.value * 1e-3) / 1e9,
+                    "note": "achieved = bytes that must move / time: the conditioning-prefix K/V of the sample_n rows of a shape "
+                            "is read once per shape (SURVEY §7 item 5); per_row_formula_* applies SURVEY §8d's per-row byte count",
+                    "share_of_ar_pass": a_ms.value / pe0.elapsed_time(pe1),
+                    "how": "CUDA events around every attention launch of one eager AR pass over the same batch, right after "
+                           "the timed region (the timed region replays the step as a CUDA graph, where events cannot be read)"}
+        # decoder: feature grids once, then the point kernel alone
+        x_tok, _ = sampler.sample(c_dev, min(S, 8), use_graph=False, **skw)
+        dense = eng.tokens_to_dense(x_tok, empty)
+        t_pro, grid_cl = ev_time(lambda: eng.feature_grid(eng.get_code(dense)))
+        t_pts, _ = ev_time(lambda: eng.decode_points(grid_cl, xtg_dev, sigmoid=True))
+        flops = 30976.0 * B * R ** 3
+        tf32_peak = peaks["bf16_tflops"] / 2.0
+        ncu_d = ncu_capture("decoder_points")
+        roof_dec = {"kernel": "decoder_points_tc_kernel (trilinear gather + ResNet-FC MLP on tcgen05)", "bound": "tensor",
+                    "achieved": flops / (t_pts * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": flops / (t_pts * 1e-3) / 1e12 / tf32_peak,
+                    "executed_frac": 3.0 * flops / (t_pts * 1e-3) / 1e12 / tf32_peak,
+                    "peak_source": peaks["source"] + " bf16_tflops (burst: kernel timed alone) / 2 = dense TF32",
+                    "algorithmic_flop_per_point": 30976, "points": B * R ** 3, "launch_ms": t_pts,
+                    "tensor_pipe_pct_ncu": ncu_d.get("tensor_pipe_pct") if ncu_d else None,
+                    "note": "achieved counts the ALGORITHMIC 30,976 FLOP/point (SURVEY §8d); the kernel executes 3x that as "
+                            "3xTF32 split products (executed_frac); tensor_pipe_pct_ncu = sm__pipe_tensor_cycles_active of the "
+                            "committed ncu capture"}
+        breakdown = {"ar_pass_eager_ms": pe0.elapsed_time(pe1), "attention_ms": a_ms.value, "conv_prologue_ms": t_pro,
+                     "point_kernel_ms": t_pts}
 
     # ---- e2e: through the reference-facing model API with HOST buffers (pinned), copies inside the timed region
     e2e = None
@@ -358,7 +446,7 @@ def main():
         def step_e2e():
             c = c_host.to(dev, non_blocking=True)
             out_x, x, hist = model.sample(c_indices=c, z_indices=c[:, :0], max_steps=S, temperature=1.0, sample=True,
-                                          best_in_first=True, top_k=args.top_k, top_p=0.0)
+                                          best_in_first=best_first, top_k=args.top_k, top_p=args.top_p)
             # NB: early exit is part of the API; with masks off and random weights no row ends, so all S steps run
             dense = eng.tokens_to_dense(out_x, empty)
             occ = vq.engine().occupancy(dense, xtg_host.to(dev, non_blocking=True))
@@ -368,26 +456,30 @@ def main():
 
         step_e2e()
         n_e2e = max(1, min(args.steps, 3))
-        ms_e = timed(step_e2e, n_e2e)
+        ms_e, _ = timed(step_e2e, n_e2e)
         hist_bytes = 2 * B * S * 4097 * 4
         e2e = {"value": rows_total * n_e2e / (ms_e * 1e-3), "unit": "shapes/s", "steps": n_e2e,
                "h2d_bytes_per_step": int(c_host.numel() * 8 + xtg_host.numel() * 4),
                "d2h_bytes_per_step": int(tok_host.numel() * 8 + occ_host.numel() * 4 + hist_bytes),
-               "api": "ShapeFormer.sample(...) [tokens + CPU logits history like the reference] -> tokens_to_dense -> "
-                      "VQDIF occupancy; pinned host buffers"}
+               "api": "ShapeFormer.sample(...) [fresh token tensor + the reference's CPU logits history, fresh tensors] -> "
+                      "tokens_to_dense -> VQDIF occupancy; pinned host buffers for inputs/outputs"}
         model.history_device = None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sd_cpu = {k: v.detach().cpu() for k, v in model.transformer.state_dict().items()}
         vq_cpu = {k: v.detach().cpu() for k, v in vq.state_dict().items()}
-        cpu = cpu_reference_sample(args, sd_cpu, vq_cpu, cfg, pick_cpu_threads(sd_cpu, cfg))
+        arm = CpuArm(args, sd_cpu, vq_cpu, cfg)
+        for _ in range(6):          # 1 warm-up + 5 repeats of the bounded sample (about 15 s of CPU work)
+            arm.sample_once()
+        cpu = arm.result(skip=1)
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": "shapes/s", "n_gpus": world, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+               "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling,
                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload, "clocks": clk,
-               "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+               "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "roofline_decoder": roof_dec,
+               "cpu_baseline": cpu, "breakdown_ms": breakdown, "per_rank_ms_per_step": per_rank_ms,
                "stepping": "cuda graph replay of one AR step" if use_graph else "eager launches"}
         emit(out)
     if world > 1:

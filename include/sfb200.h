@@ -7,8 +7,10 @@
  *
  * Conventions:
  *   - every pointer is a DEVICE pointer borrowed from the caller (torch `data_ptr()`), kept alive by the caller;
- *   - the library never allocates device memory, never synchronises, never throws; all work is enqueued on `stream`
- *     (a `cudaStream_t` passed as void*);
+ *   - the library never allocates device memory, never synchronises a stream, never throws; all work is enqueued on
+ *     `stream` (a `cudaStream_t` passed as void*).  The only host-side resources it owns are those of an sfb200_ar handle
+ *     (a captured step graph, CUDA events, and a few hundred bytes of pinned staging for the per-batch row lists;
+ *     sfb200_ar_begin_shared waits on the EVENT of the handle's previous staging copy, never on the stream);
  *   - return value 0 = ok, negative = SFB200_E_* (see sfb200_error_string); CUDA launch errors are returned as
  *     SFB200_E_CUDA with the message available from sfb200_last_cuda_error();
  *   - indices are int64 (the reference's torch.long), activations / weights fp32, row-major contiguous.

@@ -2,8 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY.  Nothing under ``shapeformer_b200/`` may import this module; it is used by
 ``tests/golden/make_golden.py`` (fixture generation) and by the ``-m "not gpu"`` tests that pin ``oracle/sf_oracle.py``
-against the reference's own modules.  ``/root/reference`` does not exist on the GPU box, so everything that needs this
-shim is skipped there (``available()`` returns False).
+against the reference's own modules, and by ``bench.py``'s CPU legs (``--impl reference`` / ``cpu_baseline``).
+``/root/reference`` does not exist on the GPU box: there the shim resolves to ``oracle/_ref`` (a git-ignored copy of the
+reference's ``*.py`` made by ``oracle/make_ref.py`` at build time); when neither exists ``available()`` returns False.
 
 The reference imports a number of packages that are not installed here (``pytorch_lightning``, ``torch_scatter``,
 ``h5py``, ``igl``, ``mcubes``, ``fresnel``, ``matplotlib``, ``skimage`` ...), none of which is touched by the hot path
@@ -16,7 +17,18 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SFB200_REFERENCE_ROOT", "/root/reference")
+def _find_root():
+    """$SFB200_REFERENCE_ROOT, else /root/reference (build container), else oracle/_ref (the git-ignored copy made by
+    oracle/make_ref.py, which is what exists on the GPU box)."""
+    env = os.environ.get("SFB200_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/shapeformer"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REFERENCE_ROOT = _find_root()
 
 _MOCK_ROOTS = ("h5py", "igl", "mcubes", "fresnel", "matplotlib", "mpl_toolkits", "skimage", "trimesh", "plyfile",
                "open3d", "seaborn", "pathos", "bashlex", "imageio", "PIL", "cv2", "sklearn", "wandb", "omegaconf")

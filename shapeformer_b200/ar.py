@@ -78,22 +78,29 @@ class ARSampler:
         self.spec, self.end_tokens = dict(spec), tuple(int(e) for e in end_tokens)
         self.device = device or weights_blob.device
         self.max_rows, self.max_cond, self.max_steps = max_rows, max_cond, max_steps
-        self.max_len = max_cond + max_steps + 1  # + the position pre-computed for the step after the last one
-        if self.max_len > spec["block_size"]:
-            raise _lib.Sfb200Error(
-                f"L_cond + max_steps + 1 = {self.max_len} exceeds block_size {spec['block_size']}: the reference's "
-                f"overflow crop (shapeformer.py:73-76) is not reproduced (SURVEY.md App. C-3)")
+        # the last token / K,V / pos_emb index touched is L_cond + max_steps - 1.  The reference's call site uses
+        # max_steps = 512 with block_size 812 and L_cond up to 406: the capacity is clamped to block_size and sample()
+        # raises only if a batch actually reaches the limit before every row has ended (the reference's overflow crop,
+        # shapeformer.py:73-76, is buggy — SURVEY.md App. C-3 — and is not reproduced).
+        self.max_len = min(max_cond + max_steps, spec["block_size"])
+        if max_cond >= self.max_len:
+            raise _lib.Sfb200Error(f"L_cond {max_cond} leaves no room to generate within block_size {spec['block_size']}")
         self.keep_history = bool(keep_history)
         self.chunk_steps = int(chunk_steps)
         prefill_rows = max(1, min(max_rows, prefill_tokens // max(1, max_cond)))
         self.cfg = _cfg_struct(spec, self.end_tokens, max_rows, self.max_len, max_steps, prefill_rows, max_cond,
                                self.keep_history)
         self.Vmax = max(spec["vocab_sizes"])
+        self._pretile = bool(pretile)
         dev = self.device
         self.weights = weights_blob
+        with torch.cuda.device(dev):
+            self._allocate(dev)
+
+    def _allocate(self, dev):
         self.kv = torch.empty(self.lib.sfb200_ar_kv_bytes(ctypes.byref(self.cfg)), dtype=torch.uint8, device=dev)
         self.ws = torch.empty(self.lib.sfb200_ar_workspace_bytes(ctypes.byref(self.cfg)), dtype=torch.uint8, device=dev)
-        self.tokens = torch.zeros(max_rows, self.max_len, 2, dtype=torch.int64, device=dev)
+        self.tokens = torch.zeros(self.max_rows, self.max_len, 2, dtype=torch.int64, device=dev)
         nh = self.lib.sfb200_ar_history_floats(ctypes.byref(self.cfg))
         self.hist = torch.empty(max(nh, 1), dtype=torch.float32, device=dev)
         self._noise = {}
@@ -107,7 +114,7 @@ class ARSampler:
         self._status_ptr = self.lib.sfb200_ar_status_ptr(self.handle)
         # batches of 9..64 rows run their linear layers from pre-split TF32 weight tiles (2x the GEMM weight bytes)
         self.pretiled = None
-        if pretile and 9 <= max_rows <= 64:
+        if self._pretile and 9 <= self.max_rows <= 64:
             n = self.lib.sfb200_ar_pretiled_floats(ctypes.byref(self.cfg))
             self.pretiled = torch.empty(n, dtype=torch.float32, device=dev)
             _lib.check(self.lib.sfb200_ar_set_pretiled(self.handle, _lib.ptr(self.pretiled), _lib.stream_ptr()),
@@ -150,7 +157,12 @@ class ARSampler:
                     q = torch.empty(B, v, dtype=torch.float32, device=self.device).exponential_(1.0, generator=generator)
                     buf[s, d, :, :v].copy_(q)
 
-    def sample(self, c_indices, max_steps, top_k=100, top_p=0.8, temperature=1.0, best_in_first=False,
+    def sample(self, *args, **kwargs):
+        """See _sample; runs with the sampler's device current (the library launches on the current device's stream)."""
+        with torch.cuda.device(self.device):
+            return self._sample(*args, **kwargs)
+
+    def _sample(self, c_indices, max_steps, top_k=100, top_p=0.8, temperature=1.0, best_in_first=False,
                mask_invalid=True, mask_invalid_completion=False, noise=None, generator=None, use_graph=True,
                stop_early=True, share_prefix=True):
         """Run the AR loop.  c_indices (B, L_c, 2) int64 (any device).  noise: optional (>= max_steps, 4, B, Vmax)
@@ -162,6 +174,9 @@ class ARSampler:
         if B > self.max_rows or L_c > self.max_cond or max_steps > self.max_steps:
             raise _lib.Sfb200Error(f"batch (B={B}, L_c={L_c}, steps={max_steps}) exceeds the sampler's capacity "
                                    f"({self.max_rows}, {self.max_cond}, {self.max_steps})")
+        steps_cap = min(max_steps, self.max_len - L_c)   # steps that fit the context window (block_size)
+        if steps_cap < 1:
+            raise _lib.Sfb200Error(f"L_cond {L_c} leaves no room to generate within block_size {self.spec['block_size']}")
         V = self.spec["vocab_sizes"]
         if int(c_indices[..., 0].max()) >= V[0] or int(c_indices[..., 1].max()) >= V[1] or int(c_indices.min()) < 0:
             raise _lib.Sfb200Error("conditioning indices out of vocabulary range")
@@ -181,9 +196,9 @@ class ARSampler:
                 row_src[b] = b
         _lib.check(self.lib.sfb200_ar_begin_shared(self.handle, B, L_c, ctypes.byref(sp),
                                                    ctypes.cast(row_src, ctypes.c_void_p), stream), "sfb200_ar_begin_shared")
-        done, steps = 0, max_steps
-        while done < max_steps:
-            n = min(self.chunk_steps, max_steps - done)
+        done, steps, ended = 0, steps_cap, -1
+        while done < steps_cap:
+            n = min(self.chunk_steps, steps_cap - done)
             slab = self._noise_buf(B)
             if noise is not None:
                 slab[:n].copy_(noise[done:done + n].to(self.device, non_blocking=True))
@@ -197,6 +212,15 @@ class ARSampler:
                 if ended >= 0:
                     steps = ended + 1
                     break
+        if steps_cap < max_steps and ended < 0:
+            if not stop_early:
+                _, ended = self._read_status()
+            if ended < 0:
+                raise _lib.Sfb200Error(
+                    f"context window exhausted: L_cond {L_c} + {steps_cap} generated tuples reached block_size "
+                    f"{self.spec['block_size']} before every row ended; the reference's overflow crop "
+                    f"(shapeformer.py:73-76) is not reproduced (SURVEY.md App. C-3)")
+            steps = ended + 1
         x = self.tokens[:B, L_c:L_c + steps]
         hist = None
         if self.keep_history:

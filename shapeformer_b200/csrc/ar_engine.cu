@@ -145,6 +145,11 @@ struct sfb200_ar {
     double prof_bytes;         // bytes that must move (conditioning prefix counted once per group when shared)
     double prof_bytes_per_row; // SURVEY §8d per-row formula (no sharing)
     int steps_host;            // steps enqueued since sfb200_ar_begin (host mirror of st[ST_STEPS])
+    // pinned staging for the per-batch row lists (leaders | duplicate rows | their sources), owned by the handle so that
+    // sfb200_ar_begin_shared never has to synchronise the stream; stage_ev marks the last copy out of it
+    int32_t *h_stage;
+    cudaEvent_t stage_ev;
+    bool stage_busy;
 };
 
 static inline const float *W_(const sfb200_ar *h, int id, int g, int l) { return h->w + weight_offset(&h->lay, id, g, l); }
@@ -212,6 +217,14 @@ int sfb200_ar_create(const sfb200_ar_config *cfg, const float *weights, void *kv
     h->Vmax = cfg->vocab[0] > cfg->vocab[1] ? cfg->vocab[0] : cfg->vocab[1];
     h->begun = false;
     h->gexec = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void **>(&h->h_stage), sizeof(int32_t) * 3 * cfg->max_rows, cudaHostAllocDefault) !=
+            cudaSuccess ||
+        cudaEventCreateWithFlags(&h->stage_ev, cudaEventDisableTiming) != cudaSuccess) {
+        set_cuda_error(cudaGetLastError(), "sfb200_ar_create: pinned staging");
+        if (h->h_stage) cudaFreeHost(h->h_stage);
+        free(h);
+        return SFB200_E_CUDA;
+    }
     *out = h;
     return SFB200_OK;
 }
@@ -220,6 +233,8 @@ void sfb200_ar_destroy(sfb200_ar *h) {
     if (!h) return;
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+    if (h->stage_ev) cudaEventDestroy(h->stage_ev);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->ev) {
         for (cudaEvent_t e : *h->ev) cudaEventDestroy(e);
         delete h->ev;
@@ -359,10 +374,16 @@ extern "C" int sfb200_ar_begin_shared(sfb200_ar *h, int B, int L_cond, const sfb
     int32_t *rm = WS_<int32_t>(h, h->buf.rowmap);
     const int32_t *rm_lead = nullptr, *rm_dst = rm + h->cfg.max_rows, *rm_src = rm + 2 * h->cfg.max_rows;
     if (n_dup > 0) {
-        SFB_CUDA_TRY(cudaMemcpyAsync(rm, lead.data(), n_lead * 4, cudaMemcpyHostToDevice, s));
-        SFB_CUDA_TRY(cudaMemcpyAsync(rm + h->cfg.max_rows, dup_dst.data(), n_dup * 4, cudaMemcpyHostToDevice, s));
-        SFB_CUDA_TRY(cudaMemcpyAsync(rm + 2 * h->cfg.max_rows, dup_src.data(), n_dup * 4, cudaMemcpyHostToDevice, s));
-        SFB_CUDA_TRY(cudaStreamSynchronize(s));   // the host vectors go out of scope (pageable staging); B ints, once per batch
+        // the row lists go through the handle's pinned staging buffer: no stream synchronisation.  The only wait is for the
+        // PREVIOUS batch's copy out of the same buffer, which finished long ago unless batches are begun back to back.
+        if (h->stage_busy) SFB_CUDA_TRY(cudaEventSynchronize(h->stage_ev));
+        const int mr = h->cfg.max_rows;
+        memcpy(h->h_stage, lead.data(), sizeof(int32_t) * n_lead);
+        memcpy(h->h_stage + mr, dup_dst.data(), sizeof(int32_t) * n_dup);
+        memcpy(h->h_stage + 2 * mr, dup_src.data(), sizeof(int32_t) * n_dup);
+        SFB_CUDA_TRY(cudaMemcpyAsync(rm, h->h_stage, sizeof(int32_t) * 3 * mr, cudaMemcpyHostToDevice, s));
+        SFB_CUDA_TRY(cudaEventRecord(h->stage_ev, s));
+        h->stage_busy = true;
         rm_lead = rm;
     }
     float *px = WS_<float>(h, h->buf.px), *px1 = WS_<float>(h, h->buf.px1), *x0 = WS_<float>(h, h->buf.x0);

@@ -342,10 +342,9 @@ static int launch_linear_t(const float *x, const float *W, const float *bias, co
                            int K, int act, cudaStream_t stream) {
     constexpr int MT = 16 * MI;
     const size_t smem = (size_t)LIN_STAGES * (MT + LIN_NT) * LIN_S * sizeof(float);
-    static bool attr_done = false;  // per template instance
-    if (!attr_done) {
+    static unsigned long long attr_done = 0;   // bit per device
+    if (first_use_on_device(attr_done)) {
         SFB_CUDA_TRY(cudaFuncSetAttribute(linear_kernel<MI, KSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
     }
     return launch_ex("linear", linear_kernel<MI, KSPLIT>, dim3((N + LIN_NT - 1) / LIN_NT, (M + MT - 1) / MT, KSPLIT), dim3(256), smem,
                      stream, dim3(1, 1, KSPLIT), x, W, bias, residual, y, M, N, K, act);
@@ -1068,10 +1067,9 @@ int launch_sample(const SampleLaunch &p, cudaStream_t s) {
     a.noise_row_stride = p.noise_row_stride > 0 ? p.noise_row_stride : p.V;
     // keys (8 B each) + the ev / compaction-list region (>= 1024 x 8 B)
     const size_t smem = (size_t)npad * 8 + ((size_t)npad * 4 > 8192 ? (size_t)npad * 4 : 8192);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_done = 0;   // bit per device
+    if (first_use_on_device(attr_done)) {
         SFB_CUDA_TRY(cudaFuncSetAttribute(ar_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12));
-        attr_done = true;
     }
     return launch_ex("ar_sample", ar_sample_kernel, dim3(p.B), dim3(SMP_THREADS), smem, s, dim3(1, 1, 1), a);
 }

@@ -83,6 +83,16 @@ static inline int launch_ex(const char *what, void (*kernel)(KArgs...), dim3 gri
     return SFB200_OK;
 }
 
+// Per-device one-time setup (cudaFuncSetAttribute is a per-device property): returns true the first time it is called with
+// this `mask` on the CURRENT device.  A benign race between host threads only repeats an idempotent setup.
+static inline bool first_use_on_device(unsigned long long &mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+    if ((mask >> dev) & 1ull) return false;
+    mask |= 1ull << dev;
+    return true;
+}
+
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }

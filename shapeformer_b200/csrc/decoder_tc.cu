@@ -278,7 +278,6 @@ int launch_decoder_points_tc(const float *grid, const float *xtg, int64_t xtg_bs
         int dev = 0;
         SFB_CUDA_TRY(cudaGetDevice(&dev));
         SFB_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        attr_done = true;
     }
     const int64_t n_tiles = ((N + 127) / 128) * B;
     int64_t ctas = (n_tiles + 1) / 2;

@@ -338,11 +338,10 @@ static int launch_tc_t(const float *x, const float *W, const float *bias, const 
                        int act, cudaStream_t stream) {
     const int n_tiles = (N + 127) / 128, m_tiles = (M + BN - 1) / BN;
     if (m_tiles > 65535) return SFB200_E_ARG;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_done = 0;   // bit per device
+    if (first_use_on_device(attr_done)) {
         SFB_CUDA_TRY(cudaFuncSetAttribute(tc_linear_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcgSmem<BN>::TOTAL));
         SFB_CUDA_TRY(cudaFuncSetAttribute(tc_linear_kernel<BN>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        attr_done = true;
     }
     const int splits = tc_pick_splits<BN>(M, N, K);
     return launch_ex("tc_linear", tc_linear_kernel<BN>, dim3(n_tiles, splits, m_tiles), dim3(TCG_THREADS), TcgSmem<BN>::TOTAL, stream,

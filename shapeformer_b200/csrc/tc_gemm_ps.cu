@@ -318,11 +318,10 @@ static int ps_max_cluster(int tiles) {
 int launch_linear_tc_ps(const float *x, const float *Wt, const float *bias, const float *residual, float *y, int M, int N, int K,
                         int act, cudaStream_t stream) {
     if (M <= 0 || M > PS_BN || N <= 0 || K <= 0 || K % 32 != 0) return SFB200_E_ARG;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_done = 0;   // bit per device
+    if (first_use_on_device(attr_done)) {
         SFB_CUDA_TRY(cudaFuncSetAttribute(tc_linear_ps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PS_SMEM));
         SFB_CUDA_TRY(cudaFuncSetAttribute(tc_linear_ps_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        attr_done = true;
     }
     const int tiles = (N + 127) / 128, nch = K / 32;
     int s = 148 / tiles;

@@ -5,10 +5,22 @@ The gather, the layout change and the per-point kernel are libsfb200 kernels.  T
 "cuDNN first, custom later") runs the reference's own op set through PyTorch/cuDNN: strict fp32 for the UNet3D, and for
 the Upsampler (80 % of the conv time) three TF32 tensor-core convolutions on hi/lo operand splits (fp32-grade results).
 """
+import functools
+
 import torch
 import torch.nn.functional as F
 
 from . import _lib
+
+
+def _on_device(fn):
+    """Run a method with the instance's CUDA device current: libsfb200 launches on torch's current stream of the current
+    device, and the function attributes / constant banks of the library are per-device state."""
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapped
 
 
 def pack_mlp_weights(sd, prefix="decoder."):
@@ -94,7 +106,7 @@ def conv_prologue(sd, x, prefix="decoder.", wsplit=None, unet_mode="fp32", up_mo
 class ImplicitDecoder:
     """decode_index for batches of code grids.  `sd`: VQDIF state dict (decoder.*, quantizer.embedding.weight).
     impl: 0 = tcgen05 tensor-core point kernel (default), 1 = fp32 FFMA point kernel (kept for cross-checking)."""
-    _active = None   # which instance's MLP weights currently sit in the library's constant bank
+    _active = {}     # device index -> instance whose MLP weights currently sit in that device's constant bank
 
     def __init__(self, sd, device, impl=0, prefix="decoder.", codebook_key="quantizer.embedding.weight", unet_mode="fp32",
                  up_mode="3xtf32"):
@@ -115,10 +127,12 @@ class ImplicitDecoder:
                 self.wsplit[k] = split_tf32(v)
 
     def _activate(self):
-        if ImplicitDecoder._active is not self:
+        key = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        if ImplicitDecoder._active.get(key) is not self:
             _lib.check(self.lib.sfb200_decoder_set_weights(_lib.ptr(self.mlp), _lib.stream_ptr()), "decoder_set_weights")
-            ImplicitDecoder._active = self
+            ImplicitDecoder._active[key] = self
 
+    @_on_device
     def get_code(self, code_ind):
         """Quantizer.get_code: (B,R,R,R) int64 -> (B,C,R,R,R) fp32."""
         B = code_ind.shape[0]
@@ -131,6 +145,7 @@ class ImplicitDecoder:
                                                _lib.stream_ptr()), "code_gather")
         return out
 
+    @_on_device
     def feature_grid(self, quant_feat):
         """(B,128,16,16,16) quantised features -> channel-last (B,64,64,64,32) decoder feature grid."""
         g = conv_prologue(self.sd, quant_feat, self.prefix, self.wsplit, self.unet_mode, self.up_mode).contiguous()
@@ -141,6 +156,7 @@ class ImplicitDecoder:
                    "grid_to_channels_last")
         return out
 
+    @_on_device
     def decode_points(self, grid_cl, Xtg, impl=None, sigmoid=False):
         """grid_cl (B,R,R,R,32), Xtg (B or 1, N, 3) in [-1,1] -> logits (B, N) (occupancy when sigmoid=True)."""
         B, R = grid_cl.shape[0], grid_cl.shape[1]
@@ -174,6 +190,7 @@ class ImplicitDecoder:
         (B,R,R,R) int64 codes -> (B, N) occupancy in [0,1]."""
         return self.decode_points(self.feature_grid(self.get_code(code_ind)), Xtg, impl, sigmoid=True)
 
+    @_on_device
     def tokens_to_dense(self, tokens, empty_index, res=16, end_tokens=(4096, 4096)):
         """filter_end_tokens + batch_sparse2dense for every row (shapeformer/common.py:50-55,171-189):
         tokens (B,T,2) int64, empty_index (B,) int64 -> (B,res,res,res) int64."""

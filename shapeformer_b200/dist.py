@@ -33,10 +33,24 @@ def broadcast_parameters(tensors, src=0):
 
 
 def gather_rows(local, out_list=None):
-    """All-gather equally-shaped per-rank row tensors; returns the list ordered by rank (row blocks in global order)."""
+    """All-gather per-rank row tensors (dim 0 = rows; row counts may differ between ranks, as row_block yields unequal blocks
+    when the group count is not a multiple of the world size); returns the list ordered by rank, each trimmed to its rank's
+    row count.  `out_list` (same-shaped preallocated buffers) is used only when every rank holds the same number of rows."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return [local]
-    if out_list is None:
-        out_list = [torch.empty_like(local) for _ in range(dist.get_world_size())]
-    dist.all_gather(out_list, local.contiguous())
-    return out_list
+    world = dist.get_world_size()
+    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    counts = [torch.empty_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c) for c in counts]
+    top = max(counts)
+    if top == min(counts):
+        if out_list is None:
+            out_list = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(out_list, local.contiguous())
+        return out_list
+    pad = local.new_zeros((top,) + tuple(local.shape[1:]))
+    pad[:local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad)
+    return [b[:c] for b, c in zip(bufs, counts)]

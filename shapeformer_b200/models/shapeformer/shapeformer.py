@@ -22,6 +22,10 @@ class ShapeFormer(nn.Module):
         self.representer = sysutil.instantiate_from_opt(representer_opt)
         assert "TupleGPT" in transformer_opt["class"]
         self.history_device = "cpu"   # the reference returns the logits history on the CPU (shapeformer.py:94)
+        # False (default): sample()/sample_indices() return FRESH tensors like the reference.  True: `x` and the history are
+        # views of the sampler's persistent buffers (device token buffer / pinned host staging) — valid only until the next
+        # sample() call of this model; opt-in for callers that consume them immediately (saves a 1 GB host copy at 64 rows).
+        self.zero_copy_outputs = False
         self.eval()
 
     @property
@@ -43,25 +47,37 @@ class ShapeFormer(nn.Module):
         rep = self.representer
         keep = self.history_device is not None
         s = self.transformer.sampler(B, L_c, max_steps, self.end_tokens, keep_history=keep)
-        x, hist = s.sample(c_indices, max_steps, top_k=top_k, top_p=top_p, temperature=temperature,
+        with torch.cuda.device(self.device):
+            x, hist = self._run_sampler(s, c_indices, max_steps, top_k, top_p, temperature, best_in_first, rep, noise,
+                                        generator)
+        if hist is None:
+            hist = [None] * tuple_n
+        elif self.history_device == "cpu":
+            with torch.cuda.device(self.device):
+                hist = [self._to_host(h, i) for i, h in enumerate(hist)]
+            if not self.zero_copy_outputs:
+                hist = [h.clone() for h in hist]
+        elif not self.zero_copy_outputs:
+            hist = [h.clone() for h in hist]
+        return (x if self.zero_copy_outputs else x.clone()), hist
+
+    @staticmethod
+    def _run_sampler(s, c_indices, max_steps, top_k, top_p, temperature, best_in_first, rep, noise, generator):
+        return s.sample(c_indices, max_steps, top_k=top_k, top_p=top_p, temperature=temperature,
                            best_in_first=best_in_first, mask_invalid=getattr(rep, "mask_invalid", True),
                            mask_invalid_completion=getattr(rep, "mask_invalid_completion", False), noise=noise,
                            generator=generator)
-        if hist is not None and self.history_device == "cpu":
-            hist = [self._to_host(h) for h in hist]
-        elif hist is None:
-            hist = [None] * tuple_n
-        return x, hist
 
     _pinned = {}
 
-    def _to_host(self, t):
-        """One D2H copy of the (B, steps, V) history slab into a reusable pinned buffer (the reference pays a
-        synchronising .cpu() per sub-step)."""
-        key = (tuple(t.shape), t.dtype)
+    def _to_host(self, t, slot):
+        """One D2H copy of the (B, steps, V) history slab of tuple element `slot` into a reusable pinned staging buffer
+        (the reference pays a synchronising .cpu() per sub-step)."""
+        key = (slot, tuple(t.shape), t.dtype)
         buf = ShapeFormer._pinned.get(key)
         if buf is None:
-            ShapeFormer._pinned.clear() if len(ShapeFormer._pinned) > 4 else None
+            for k in [k for k in ShapeFormer._pinned if k[0] == slot]:
+                del ShapeFormer._pinned[k]          # one staging buffer per tuple element
             buf = torch.empty(t.shape, dtype=t.dtype).pin_memory()
             ShapeFormer._pinned[key] = buf
         buf.copy_(t, non_blocking=True)

@@ -53,6 +53,14 @@ class CondTupleGPT(nn.Module):
         self._samplers = {}
         # reference checkpoints also carry the causal-mask buffers (blocks.g.l.attn.mask): accept and drop them
         self._register_load_state_dict_pre_hook(self._drop_masks)
+        # fires for direct AND nested loads (a parent ShapeFormer.load_state_dict recurses through
+        # _load_from_state_dict, never through this module's load_state_dict): new weights invalidate the packed blob,
+        # the samplers built on it and their captured graphs
+        self.register_load_state_dict_post_hook(self._invalidate)
+
+    @staticmethod
+    def _invalidate(module, incompatible_keys):
+        module._packed, module._samplers = None, {}
 
     @staticmethod
     def _drop_masks(state_dict, prefix, *args):
@@ -72,11 +80,6 @@ class CondTupleGPT(nn.Module):
     def get_block_size(self):
         return self.block_size
 
-    def load_state_dict(self, *a, **k):
-        out = super().load_state_dict(*a, **k)
-        self._packed, self._samplers = None, {}
-        return out
-
     # ------------------------------------------------------------------------------------------------------------------
     def packed_weights(self):
         """fp32 weight blob in the library's layout on this module's CUDA device (built once, after loading)."""
@@ -90,12 +93,15 @@ class CondTupleGPT(nn.Module):
         return self._packed
 
     def sampler(self, rows, L_cond, max_steps, end_tokens, keep_history=True):
-        """An ARSampler with capacity for this batch shape (cached and reused)."""
-        key = (rows, L_cond, max_steps, tuple(end_tokens), keep_history)
+        """An ARSampler with CAPACITY for this batch (cached and reused): the conditioning length is bucketed to a multiple
+        of 64 so that shapes with different L_cond share one KV cache, one workspace and one captured step graph (the
+        sampler accepts any L_c <= max_cond, B <= max_rows)."""
+        cap = min(-(-max(int(L_cond), 1) // 64) * 64, self.block_size - 1)
+        key = (rows, cap, max_steps, tuple(end_tokens), keep_history)
         s = self._samplers.get(key)
         if s is None:
             self._samplers.clear()   # one live KV cache at a time
-            s = _ar.ARSampler(self.packed_weights(), self.spec, end_tokens, max_rows=rows, max_cond=L_cond,
+            s = _ar.ARSampler(self.packed_weights(), self.spec, end_tokens, max_rows=rows, max_cond=cap,
                               max_steps=max_steps, keep_history=keep_history)
             self._samplers[key] = s
         return s

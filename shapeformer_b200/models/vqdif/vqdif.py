@@ -21,16 +21,23 @@ class VQDIF(nn.Module):
         self.requires_grad_(False)
         self.eval()
         self._engine = None
+        # nested loads (a parent ShapeFormer checkpoint carries representer.vqvae_model.encoder.*) go through
+        # _load_from_state_dict, so the key filter and the engine invalidation are hooks, not a load_state_dict override
+        self._register_load_state_dict_pre_hook(self._drop_unbuilt)
+        self.register_load_state_dict_post_hook(self._invalidate)
+
+    def _drop_unbuilt(self, state_dict, prefix, *args):
+        if self.encoder is None:
+            for k in [k for k in state_dict if k.startswith(prefix + "encoder.")]:
+                del state_dict[k]
+
+    @staticmethod
+    def _invalidate(module, incompatible_keys):
+        module._engine = None
 
     @property
     def device(self):
         return self.decoder.fc_out.weight.device
-
-    def load_state_dict(self, state_dict, strict=True):
-        own = {k: v for k, v in state_dict.items() if not k.startswith("encoder.")}
-        out = super().load_state_dict(own, strict=strict)
-        self._engine = None
-        return out
 
     def engine(self):
         if self._engine is None or self._engine.device != self.device:

@@ -25,6 +25,9 @@ def _worker(rank, world, port, q):
         pad[:hi - lo] = local
         rows = torch.cat([t[t[:, 0] >= 0] for t in sdist.gather_rows(pad)])
         ok = ok and torch.equal(rows[:, 0], torch.arange(12))
+        # unequal blocks gathered directly (counts exchanged, padded internally, trimmed per rank)
+        parts = sdist.gather_rows(local)
+        ok = ok and [p.shape[0] for p in parts] == [8, 4] and torch.equal(torch.cat(parts)[:, 0], torch.arange(12))
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()

@@ -80,3 +80,45 @@ def test_tf32_split_and_fp32_conv_prologue_on_cpu():
     sd = synth.vqdif_state_dict(seed=6)
     x = O.get_code(sd, synth.code_grids(1, seed=1))
     assert torch.equal(decoder.conv_prologue(sd, x, up_mode="fp32"), O.upsampler(sd, O.unet3d(sd, x)))
+
+
+def test_full_checkpoint_loads_through_the_parent_and_invalidates_caches():
+    """A reference ShapeFormer checkpoint (transformer.* incl. attn.mask buffers, representer.vqvae_model.{encoder,decoder,
+    quantizer}.*) loads STRICTLY through the parent module, and the nested load resets the packed-weight / sampler / decoder
+    engine caches (nn.Module recursion bypasses the children's load_state_dict, so these are hooks)."""
+    from shapeformer_b200.models.shapeformer.shapeformer import ShapeFormer
+    cfg = synth.TINY_GPT
+    pre = "shapeformer_b200.models."
+    vq_opt = {"class": pre + "vqdif.vqdif.VQDIF", "kwargs": dict(
+        decoder_opt={"class": pre + "vqdif.dec.LocalDecoder",
+                     "kwargs": dict(sample_mode="bilinear", hidden_size=32, c_dim=32, unet3d=True,
+                                    unet3d_kwargs=dict(num_levels=3, f_maps=128, in_channels=128, out_channels=128),
+                                    upsampler=True, upsampler_kwargs=dict(in_channels=128, upsampler_steps=2))},
+        quantizer_opt={"class": pre + "vqdif.quantizer.Quantizer", "kwargs": dict(vocab_size=4096, n_embd=128)})}
+    model = ShapeFormer(tuple_n=2, block_size=cfg["block_size"], end_tokens=[4096, 4096], vocab_sizes=list(cfg["vocab_sizes"]),
+                        extra_vocab_sizes=list(cfg["extra_vocab_sizes"]),
+                        transformer_opt={"class": pre + "shapeformer.transformer.mingpt.CondTupleGPT",
+                                         "kwargs": dict(tuple_n=2, vocab_sizes=cfg["vocab_sizes"],
+                                                        extra_vocab_sizes=cfg["extra_vocab_sizes"], n_layers=cfg["n_layers"],
+                                                        block_size=cfg["block_size"], n_head=cfg["n_head"],
+                                                        n_embd=cfg["n_embd"])},
+                        representer_opt={"class": pre + "shapeformer.representers.AR_N",
+                                         "kwargs": dict(block_size=cfg["block_size"], end_tokens=[4096, 4096],
+                                                        vqvae_opt=vq_opt)})
+    ckpt = {"transformer." + k: v for k, v in synth.gpt_state_dict(cfg, seed=5).items()}
+    bs = cfg["block_size"]
+    for g, nl in enumerate(cfg["n_layers"]):
+        for l in range(nl):
+            ckpt[f"transformer.blocks.{g}.{l}.attn.mask"] = torch.tril(torch.ones(bs, bs)).view(1, 1, bs, bs)
+    vsd = synth.vqdif_state_dict(seed=5)
+    ckpt.update({"representer.vqvae_model." + k: v for k, v in vsd.items()})
+    vq = model.representer.vqvae_model
+    for k, v in vq.quantizer.state_dict().items():      # EMA buffers of the quantiser
+        ckpt.setdefault("representer.vqvae_model.quantizer." + k, v.clone())
+    if vq.encoder is None:   # keys of the reference's encoder (not built): accepted and dropped
+        ckpt["representer.vqvae_model.encoder.fc_pos.weight"] = torch.zeros(64, 3)
+    model.transformer._packed, model.transformer._samplers, vq._engine = object(), {"stale": 1}, object()
+    model.load_state_dict(ckpt, strict=True)
+    assert model.transformer._packed is None and model.transformer._samplers == {} and vq._engine is None
+    assert torch.equal(model.transformer.tok_embs[0].weight, ckpt["transformer.tok_embs.0.weight"])
+    assert torch.equal(vq.decoder.fc_out.weight, vsd["decoder.fc_out.weight"])
