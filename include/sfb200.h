@@ -179,6 +179,12 @@ int sfb200_ar_steps(sfb200_ar *h, int n_steps, const float *noise, int use_graph
  * (0-based) at which all rows had ended, or -1.  Returns a device pointer to int32[4]. */
 const int32_t *sfb200_ar_status_ptr(const sfb200_ar *h);
 
+/* Device pointer (inside the workspace) to the log-probabilities of the sampled tokens, (max_rows, max_steps, 2) fp32:
+ * entry [b][j][i] = log_softmax(masked logits of sub-step i of step j)[sampled token] — what compute_log_probs
+ * (shapeformer/shapeformer.py:407-418) derives from the logits history, accumulated on the device so that ranking the sample_n
+ * completions does not need the (B, steps, 4097) x 2 history at all.  Valid for steps executed since sfb200_ar_begin. */
+const float *sfb200_ar_logprob_ptr(const sfb200_ar *h);
+
 /* Measurement aid for bench.py: when enabled (eager stepping only), every attention launch of sfb200_ar_steps is bracketed
  * by CUDA events on `stream`.  sfb200_ar_profile_read must be called after the stream has been synchronised; it returns the
  * summed device time (ms), the number of launches and the ALGORITHMIC bytes of those launches
@@ -208,6 +214,16 @@ int sfb200_tc_pretile(const float *W, float *Wt, int N, int K, void *stream);
 int sfb200_linear_tc_ps(const float *x, const float *Wt, const float *bias, const float *residual, float *y, int M, int N, int K,
                         int act, void *stream);
 
+/* One nn.Linear (optionally preceded by a LayerNorm over the K input features) through the persistent GEMM-chain kernel the
+ * sampler's decode step uses for <= 64 rows (csrc/ar_chain.cu): y = act(LN?(x) W^T + bias) + residual, 3xTF32 on tcgen05 from
+ * the fp32 weights (TMA-streamed), split-K reduced through L2 in a fixed order.  Replaces ln + nn.Linear of Block.forward
+ * (transformer/mingpt.py:108-111) and of the heads (:222-231).  M <= 64, K % 32 == 0, K <= 4096; `workspace` =
+ * sfb200_chain_workspace_bytes() bytes of device memory whose first 256 bytes are ZERO before the first call (the kernel
+ * leaves them zero); ln_w / ln_b both NULL for a plain linear layer.  W must be 16-byte aligned. */
+int64_t sfb200_chain_workspace_bytes(void);
+int sfb200_chain_linear(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
+                        int act, const float *ln_w, const float *ln_b, void *workspace, void *stream);
+
 /* Development aid: register a device buffer of 16 uint64; CTA (0,0) of sfb200_linear_tc_ps stamps %globaltimer (ns) at its
  * phase boundaries (slots documented in tc_gemm_ps.cu).  NULL unregisters. */
 int sfb200_debug_ps_timeline(void *buf16);
@@ -221,6 +237,14 @@ int sfb200_layernorm(const float *x, const float *w, const float *b, float *y, i
  * out (B, d).  part: workspace for split-KV partials (B*H*n_split*(64+2) floats) or NULL when n_split == 1. */
 int sfb200_attn_decode(const float *qkv, float *kcache, float *vcache, float *out, float *part, int B, int H, int max_len,
                        int pos, const int32_t *pos_dev, int n_split, void *stream);
+
+/* sfb200_attn_decode for batches made of contiguous groups of `group` rows (2, 4, 6 or 8) whose first `shared_len` cached
+ * positions hold identical K/V (the reference expands one conditioning to sample_n rows, shapeformer/shapeformer.py:229): the
+ * shared prefix is read from the group's FIRST row once per (group, head) and scored against all `group` queries; every row's
+ * own positions [shared_len, pos) and the new position (appended) follow per row.  TMA bulk copies into shared memory.
+ * part: B*H*3*66 floats of scratch; counters: B*H int32, ZERO before the first call (left zero by every call). */
+int sfb200_attn_decode_grouped(const float *qkv, float *kcache, float *vcache, float *out, float *part, int32_t *counters, int B,
+                               int H, int max_len, int pos, int group, int shared_len, void *stream);
 
 /* Causal attention over T new positions (prefill) + KV-cache fill.  qkv (B, T, 3d); writes k,v to cache [0,T). out (B,T,d) */
 int sfb200_attn_prefill(const float *qkv, float *kcache, float *vcache, float *out, int B, int H, int T, int max_len,

@@ -63,6 +63,7 @@ SIGNATURES = {
     "sfb200_ar_begin_shared": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ArSampling), vp, vp]),
     "sfb200_ar_steps": (ctypes.c_int, [vp, ctypes.c_int, vp, ctypes.c_int, vp]),
     "sfb200_ar_status_ptr": (vp, [vp]),
+    "sfb200_ar_logprob_ptr": (vp, [vp]),
     "sfb200_ar_profile": (ctypes.c_int, [vp, ctypes.c_int]),
     "sfb200_ar_profile_read": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
                                               ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
@@ -71,10 +72,15 @@ SIGNATURES = {
     "sfb200_tc_pretiled_floats": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int]),
     "sfb200_tc_pretile": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp]),
     "sfb200_linear_tc_ps": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
+    "sfb200_chain_workspace_bytes": (ctypes.c_int64, []),
+    "sfb200_chain_linear": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp,
+                                           vp, vp]),
     "sfb200_debug_ps_timeline": (ctypes.c_int, [vp]),
     "sfb200_layernorm": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp]),
     "sfb200_attn_decode": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,
                                           ctypes.c_int, vp]),
+    "sfb200_attn_decode_grouped": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                  ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
     "sfb200_attn_prefill": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
     "sfb200_ar_sample": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(ArSampling), vp]),

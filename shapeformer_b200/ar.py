@@ -5,6 +5,7 @@ Replaces the body of ShapeFormer.sample_indices (reference shapeformer/models/sh
 PyTorch is used for memory, streams and RNG only; every arithmetic step runs in the CUDA library.
 """
 import ctypes
+import os
 
 import torch
 
@@ -112,9 +113,15 @@ class ARSampler:
                    "sfb200_ar_create")
         self.handle = h
         self._status_ptr = self.lib.sfb200_ar_status_ptr(self.handle)
-        # batches of 9..64 rows run their linear layers from pre-split TF32 weight tiles (2x the GEMM weight bytes)
+        off = (self.lib.sfb200_ar_logprob_ptr(self.handle) - self.ws.data_ptr()) // 4
+        self.logp = self.ws.view(torch.float32)[off:off + self.max_rows * self.max_steps * 2].view(
+            self.max_rows, self.max_steps, 2)
+        self.last_log_prob = None
+        # decode steps of <= 64 rows run the persistent GEMM-chain kernel straight from the fp32 blob (csrc/ar_chain.cu).  Only
+        # with SFB200_CHAIN=0 (per-GEMM kernels) do batches of 9..64 rows use pre-split TF32 weight tiles (2x the weight bytes)
         self.pretiled = None
-        if self._pretile and 9 <= self.max_rows <= 64:
+        chain = os.environ.get("SFB200_CHAIN", "1")[:1] != "0"
+        if self._pretile and not chain and 9 <= self.max_rows <= 64:
             n = self.lib.sfb200_ar_pretiled_floats(ctypes.byref(self.cfg))
             self.pretiled = torch.empty(n, dtype=torch.float32, device=dev)
             _lib.check(self.lib.sfb200_ar_set_pretiled(self.handle, _lib.ptr(self.pretiled), _lib.stream_ptr()),
@@ -222,6 +229,9 @@ class ARSampler:
                     f"(shapeformer.py:73-76) is not reproduced (SURVEY.md App. C-3)")
             steps = ended + 1
         x = self.tokens[:B, L_c:L_c + steps]
+        # log-softmax(masked logits)[token] of every sampled tuple element, accumulated by the sampling kernel: the input of
+        # the reference's ranking (compute_log_probs, shapeformer.py:407-418) without the logits history
+        self.last_log_prob = self.logp[:B, :steps]
         hist = None
         if self.keep_history:
             n0 = self.max_rows * self.max_steps * V[0]

@@ -75,8 +75,13 @@ static int64_t weight_offset(const Layout *L, int id, int g, int l) {
 struct Buffers {   // byte offsets into the workspace
     int64_t st, rowmap, x0, x1, h, qkv, att, ff, logits[2], part;
     int64_t px, px1, ph, pqkv, pff;
+    int64_t logp;                           // (max_rows, max_steps, 2) log-probabilities of the sampled tokens
+    int64_t att_cnt;                        // grouped attention: arrival counters per (row, head)
+    int64_t ch_bar, ch_stats, ch_scratch;   // GEMM-chain kernel: barrier counters, LayerNorm row statistics, split-K partials
     int64_t total;
 };
+
+constexpr int CHAIN_MAX_GRID = 160;    // CTAs the chain scratch is sized for (one per SM; B200 has 148)
 
 static int pick_nsplit(int B, int H) {
     int n = (2 * 148 + B * H - 1) / (B * H);
@@ -107,6 +112,11 @@ static void carve(const sfb200_ar_config *c, Buffers *b) {
     b->ph = take(P * d * F);
     b->pqkv = take(P * 3 * d * F);
     b->pff = take(P * 4 * d * F);
+    b->logp = take(B * (int64_t)c->max_steps * 2 * F);
+    b->att_cnt = take(B * c->n_head * 4);
+    b->ch_bar = take((CH_MAX_BARRIERS + 1) * 4);
+    b->ch_stats = take(64 * ((d + 511) / 512) * 2 * F);
+    b->ch_scratch = take((int64_t)chain_scratch_floats(CHAIN_MAX_GRID) * F);
     b->total = o;
 }
 
@@ -150,6 +160,11 @@ struct sfb200_ar {
     int32_t *h_stage;
     cudaEvent_t stage_ev;
     bool stage_busy;
+    // GEMM-chain kernel (ar_chain.cu): one TMA tensor map per GEMM weight, built on first use
+    TensorMapBlob *maps;       // [n_blocks][QKV, PROJ, FC1, FC2] then the two heads
+    bool maps_ready;
+    int use_chain;             // decode steps of <= 64 rows run the persistent chain kernel (SFB200_CHAIN=0 disables)
+    int use_grouped_attn;      // contiguous groups of identical conditionings use attn_grouped.cu (SFB200_ATTN_GROUPED=0 disables)
 };
 
 static inline const float *W_(const sfb200_ar *h, int id, int g, int l) { return h->w + weight_offset(&h->lay, id, g, l); }
@@ -225,6 +240,12 @@ int sfb200_ar_create(const sfb200_ar_config *cfg, const float *weights, void *kv
         free(h);
         return SFB200_E_CUDA;
     }
+    {
+        const char *e = getenv("SFB200_CHAIN");
+        h->use_chain = (e && e[0] == '0') ? 0 : 1;
+        e = getenv("SFB200_ATTN_GROUPED");
+        h->use_grouped_attn = (e && e[0] == '0') ? 0 : 1;
+    }
     *out = h;
     return SFB200_OK;
 }
@@ -233,6 +254,7 @@ void sfb200_ar_destroy(sfb200_ar *h) {
     if (!h) return;
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+    if (h->maps) free(h->maps);
     if (h->stage_ev) cudaEventDestroy(h->stage_ev);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->ev) {
@@ -243,6 +265,7 @@ void sfb200_ar_destroy(sfb200_ar *h) {
 }
 
 const int32_t *sfb200_ar_status_ptr(const sfb200_ar *h) { return h ? WS_<int32_t>(h, h->buf.st) : nullptr; }
+const float *sfb200_ar_logprob_ptr(const sfb200_ar *h) { return h ? WS_<float>(h, h->buf.logp) : nullptr; }
 
 }  // extern "C"
 
@@ -294,14 +317,12 @@ static int block_prefill(sfb200_ar *h, int g, int l, float *x, int row0, int row
     return SFB200_OK;
 }
 
-// One transformer block for the newest position of every row (decode), position read from the device state.
-static int block_step(sfb200_ar *h, int g, int l, float *x, cudaStream_t s) {
+// Decode attention of block (g, l) for the newest position (read from the device state), bracketed by events when the
+// bench's attention profiling is on.
+static int attn_step(sfb200_ar *h, int g, int l, cudaStream_t s) {
     const int d = h->cfg.n_embd, H = h->cfg.n_head, B = h->B;
     const int32_t *st = WS_<int32_t>(h, h->buf.st);
-    float *hb = WS_<float>(h, h->buf.h), *qkv = WS_<float>(h, h->buf.qkv), *att = WS_<float>(h, h->buf.att);
-    float *ff = WS_<float>(h, h->buf.ff), *part = WS_<float>(h, h->buf.part);
-    SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN1_W, g, l), W_(h, SFB200_W_LN1_B, g, l), hb, B, d, s));
-    SFB_TRY(linear(h, SFB200_W_QKV_W, g, l, hb, W_(h, SFB200_W_QKV_B, g, l), nullptr, qkv, B, 3 * d, d, 0, s));
+    float *qkv = WS_<float>(h, h->buf.qkv), *att = WS_<float>(h, h->buf.att), *part = WS_<float>(h, h->buf.part);
     const bool timed = h->prof && !h->capturing;
     if (timed) {
         if (!h->ev) h->ev = new std::vector<cudaEvent_t>();
@@ -312,8 +333,12 @@ static int block_step(sfb200_ar *h, int g, int l, float *x, cudaStream_t s) {
         }
         SFB_CUDA_TRY(cudaEventRecord((*h->ev)[h->ev_used], s));
     }
-    SFB_TRY(launch_attn_decode(qkv, kcache(h, g, l, 0), vcache(h, g, l, 0), att, part, B, H, h->cfg.max_len, 0, st,
-                               h->n_split, s, h->attn_group, 0, g == 1 ? -1 : 0));
+    if (h->attn_group > 1 && h->use_grouped_attn)
+        SFB_TRY(launch_attn_grouped(qkv, kcache(h, g, l, 0), vcache(h, g, l, 0), att, part, WS_<int>(h, h->buf.att_cnt), B, H,
+                                    h->cfg.max_len, 0, st, h->attn_group, 0, g == 1 ? -1 : 0, s));
+    else
+        SFB_TRY(launch_attn_decode(qkv, kcache(h, g, l, 0), vcache(h, g, l, 0), att, part, B, H, h->cfg.max_len, 0, st,
+                                   h->n_split, s, h->attn_group, 0, g == 1 ? -1 : 0));
     if (timed) {
         SFB_CUDA_TRY(cudaEventRecord((*h->ev)[h->ev_used + 1], s));
         h->ev_used += 2;
@@ -328,6 +353,17 @@ static int block_step(sfb200_ar *h, int g, int l, float *x, cudaStream_t s) {
         h->prof_bytes += key_rows * 2.0 * d * 4.0 + (double)B * 4.0 * d * 4.0;
         h->prof_bytes_per_row += (double)B * (2.0 * pos * d * 4.0 + 4.0 * d * 4.0);
     }
+    return SFB200_OK;
+}
+
+// One transformer block for the newest position of every row (decode) as separate kernels (rows > 64, or SFB200_CHAIN=0).
+static int block_step(sfb200_ar *h, int g, int l, float *x, cudaStream_t s) {
+    const int d = h->cfg.n_embd, B = h->B;
+    float *hb = WS_<float>(h, h->buf.h), *qkv = WS_<float>(h, h->buf.qkv), *att = WS_<float>(h, h->buf.att);
+    float *ff = WS_<float>(h, h->buf.ff);
+    SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN1_W, g, l), W_(h, SFB200_W_LN1_B, g, l), hb, B, d, s));
+    SFB_TRY(linear(h, SFB200_W_QKV_W, g, l, hb, W_(h, SFB200_W_QKV_B, g, l), nullptr, qkv, B, 3 * d, d, 0, s));
+    SFB_TRY(attn_step(h, g, l, s));
     SFB_TRY(linear(h, SFB200_W_PROJ_W, g, l, att, W_(h, SFB200_W_PROJ_B, g, l), x, x, B, d, d, 0, s));
     SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN2_W, g, l), W_(h, SFB200_W_LN2_B, g, l), hb, B, d, s));
     SFB_TRY(linear(h, SFB200_W_FC1_W, g, l, hb, W_(h, SFB200_W_FC1_B, g, l), nullptr, ff, B, 4 * d, d, 1, s));
@@ -335,12 +371,105 @@ static int block_step(sfb200_ar *h, int g, int l, float *x, cudaStream_t s) {
     return SFB200_OK;
 }
 
+// ---- persistent GEMM-chain path -------------------------------------------------------------------------------------
+static int chain_map_index(const sfb200_ar *h, int wid, int g, int l) {
+    const int nb = h->cfg.n_layers[0] + h->cfg.n_layers[1];
+    if (wid == SFB200_W_HEAD_W) return nb * 4 + g;
+    const int li = (g == 0 ? 0 : h->cfg.n_layers[0]) + l;
+    const int k = wid == SFB200_W_QKV_W ? 0 : wid == SFB200_W_PROJ_W ? 1 : wid == SFB200_W_FC1_W ? 2 : 3;
+    return li * 4 + k;
+}
+
+static int chain_build_maps(sfb200_ar *h) {
+    if (h->maps_ready) return SFB200_OK;
+    const int d = h->cfg.n_embd, nb = h->cfg.n_layers[0] + h->cfg.n_layers[1];
+    if (!h->maps) {
+        h->maps = static_cast<TensorMapBlob *>(aligned_alloc(64, sizeof(TensorMapBlob) * (size_t)(nb * 4 + 2)));
+        if (!h->maps) return SFB200_E_ARG;
+    }
+    for (int g = 0; g < 2; ++g) {
+        for (int l = 0; l < h->cfg.n_layers[g]; ++l) {
+            SFB_TRY(chain_weight_map(W_(h, SFB200_W_QKV_W, g, l), 3 * d, d, &h->maps[chain_map_index(h, SFB200_W_QKV_W, g, l)]));
+            SFB_TRY(chain_weight_map(W_(h, SFB200_W_PROJ_W, g, l), d, d, &h->maps[chain_map_index(h, SFB200_W_PROJ_W, g, l)]));
+            SFB_TRY(chain_weight_map(W_(h, SFB200_W_FC1_W, g, l), 4 * d, d, &h->maps[chain_map_index(h, SFB200_W_FC1_W, g, l)]));
+            SFB_TRY(chain_weight_map(W_(h, SFB200_W_FC2_W, g, l), d, 4 * d, &h->maps[chain_map_index(h, SFB200_W_FC2_W, g, l)]));
+        }
+        SFB_TRY(chain_weight_map(W_(h, SFB200_W_HEAD_W, g, 0), h->cfg.vocab[g], d, &h->maps[chain_map_index(h, SFB200_W_HEAD_W, g, 0)]));
+    }
+    h->maps_ready = true;
+    return SFB200_OK;
+}
+
+static bool chain_active(const sfb200_ar *h) { return h->use_chain && h->B <= 64 && chain_grid_size() > 0; }
+
+static void chain_gemm(sfb200_ar *h, ChainArgs &a, int wid, int g, int l, const float *x, const float *ln_g, const float *ln_b,
+                       const float *bias, const float *residual, float *y, bool stats_out, int N, int K, int act,
+                       int wait_before) {
+    const int p = a.n_phases++;
+    int grid = chain_grid_size();
+    if (grid > CHAIN_MAX_GRID) grid = CHAIN_MAX_GRID;
+    ChainPhase &ph = a.ph[p];
+    a.wmap[p] = h->maps[chain_map_index(h, wid, g, l)];
+    ph.x = x; ph.ln_g = ln_g; ph.ln_b = ln_b;
+    ph.stats_in = ln_g ? WS_<float>(h, h->buf.ch_stats) : nullptr;
+    ph.bias = bias; ph.residual = residual; ph.y = y;
+    ph.stats_out = stats_out ? WS_<float>(h, h->buf.ch_stats) : nullptr;
+    ph.N = N; ph.K = K; ph.act = act; ph.wait_before = wait_before;
+    chain_plan(N, K, grid, &ph.tiles, &ph.splits);
+}
+
+// All blocks of group g (+ its head) for the newest position: n + 1 chain launches interleaved with n attention launches.
+static int group_step_chain(sfb200_ar *h, int g, float *x, float *logits, cudaStream_t s) {
+    const int d = h->cfg.n_embd, nl = h->cfg.n_layers[g];
+    float *qkv = WS_<float>(h, h->buf.qkv), *att = WS_<float>(h, h->buf.att), *ff = WS_<float>(h, h->buf.ff);
+    ChainArgs a;
+    auto reset = [&]() {
+        memset(&a, 0, sizeof(a));
+        a.M = h->B;
+        a.scratch = WS_<float>(h, h->buf.ch_scratch);
+        a.bar = WS_<unsigned int>(h, h->buf.ch_bar);
+    };
+    // launch 0: row statistics of x (written by the embedding kernels) -> LN1 -> QKV of the first block
+    reset();
+    {
+        ChainPhase &ph = a.ph[a.n_phases++];
+        ph.residual = x; ph.stats_out = WS_<float>(h, h->buf.ch_stats); ph.N = d; ph.tiles = 0; ph.splits = 0;
+    }
+    chain_gemm(h, a, SFB200_W_QKV_W, g, 0, x, W_(h, SFB200_W_LN1_W, g, 0), W_(h, SFB200_W_LN1_B, g, 0),
+               W_(h, SFB200_W_QKV_B, g, 0), nullptr, qkv, false, 3 * d, d, 0, 1);
+    SFB_TRY(launch_chain(a, s));
+    for (int l = 0; l < nl; ++l) {
+        SFB_TRY(attn_step(h, g, l, s));
+        reset();
+        chain_gemm(h, a, SFB200_W_PROJ_W, g, l, att, nullptr, nullptr, W_(h, SFB200_W_PROJ_B, g, l), x, x, true, d, d, 0, 0);
+        chain_gemm(h, a, SFB200_W_FC1_W, g, l, x, W_(h, SFB200_W_LN2_W, g, l), W_(h, SFB200_W_LN2_B, g, l),
+                   W_(h, SFB200_W_FC1_B, g, l), nullptr, ff, false, 4 * d, d, 1, 1);
+        chain_gemm(h, a, SFB200_W_FC2_W, g, l, ff, nullptr, nullptr, W_(h, SFB200_W_FC2_B, g, l), x, x, true, d, 4 * d, 0, 1);
+        if (l + 1 < nl)
+            chain_gemm(h, a, SFB200_W_QKV_W, g, l + 1, x, W_(h, SFB200_W_LN1_W, g, l + 1), W_(h, SFB200_W_LN1_B, g, l + 1),
+                       W_(h, SFB200_W_QKV_B, g, l + 1), nullptr, qkv, false, 3 * d, d, 0, 1);
+        else
+            chain_gemm(h, a, SFB200_W_HEAD_W, g, 0, x, W_(h, SFB200_W_HEAD_LN_W, g, 0), W_(h, SFB200_W_HEAD_LN_B, g, 0), nullptr,
+                       nullptr, logits, false, h->cfg.vocab[g], d, 0, 1);
+        SFB_TRY(launch_chain(a, s));
+    }
+    return SFB200_OK;
+}
+
+static int group_step(sfb200_ar *h, int g, float *x, float *logits, cudaStream_t s);
+
 static int head(sfb200_ar *h, int g, const float *x, float *logits, int rows, cudaStream_t s) {
     const int d = h->cfg.n_embd;
     float *hb = WS_<float>(h, h->buf.h);
     SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_HEAD_LN_W, g, 0), W_(h, SFB200_W_HEAD_LN_B, g, 0), hb, rows, d, s));
     SFB_TRY(linear(h, SFB200_W_HEAD_W, g, 0, hb, nullptr, nullptr, logits, rows, h->cfg.vocab[g], d, 0, s));
     return SFB200_OK;
+}
+
+static int group_step(sfb200_ar *h, int g, float *x, float *logits, cudaStream_t s) {
+    if (chain_active(h)) return group_step_chain(h, g, x, logits, s);
+    for (int l = 0; l < h->cfg.n_layers[g]; ++l) SFB_TRY(block_step(h, g, l, x, s));
+    return head(h, g, x, logits, h->B, s);
 }
 
 extern "C" int sfb200_ar_begin_shared(sfb200_ar *h, int B, int L_cond, const sfb200_ar_sampling *sp, const int32_t *row_src,
@@ -355,6 +484,11 @@ extern "C" int sfb200_ar_begin_shared(sfb200_ar *h, int B, int L_cond, const sfb
     h->steps_host = 0;
     int32_t *st = WS_<int32_t>(h, h->buf.st);
     SFB_TRY(launch_state_init(st, L_cond, s));
+    SFB_CUDA_TRY(cudaMemsetAsync(WS_<int>(h, h->buf.att_cnt), 0, (size_t)h->cfg.max_rows * h->cfg.n_head * 4, s));
+    if (chain_active(h)) {
+        SFB_TRY(chain_build_maps(h));
+        SFB_CUDA_TRY(cudaMemsetAsync(WS_<unsigned int>(h, h->buf.ch_bar), 0, (CH_MAX_BARRIERS + 1) * 4, s));
+    }
     // ---- group leaders / duplicates
     std::vector<int32_t> lead, dup_dst, dup_src;
     for (int b = 0; b < B; ++b) {
@@ -432,6 +566,7 @@ static int enqueue_step(sfb200_ar *h, const float *noise, cudaStream_t s) {
     p.tokens = h->tokens; p.B = B; p.max_len = h->cfg.max_len; p.L = 0; p.L_cond = 0;
     p.end0 = h->cfg.end_tokens[0]; p.end1 = h->cfg.end_tokens[1]; p.sp = h->sp; p.st = st;
     p.noise_step_stride = 4 * draw; p.noise_row_stride = h->Vmax;
+    p.logp = WS_<float>(h, h->buf.logp); p.logp_row_stride = 2 * (int64_t)h->cfg.max_steps;
     // --- position
     p.logits = WS_<float>(h, h->buf.logits[0]); p.V = h->cfg.vocab[0]; p.tuple_i = 0;
     p.hist = h->hist; p.hist_row_stride = (int64_t)h->cfg.max_steps * h->cfg.vocab[0];
@@ -439,8 +574,7 @@ static int enqueue_step(sfb200_ar *h, const float *noise, cudaStream_t s) {
     SFB_TRY(launch_sample(p, s));
     // --- value
     SFB_TRY(launch_add_target(x0, x1, h->tokens, W_(h, SFB200_W_TOK_EMB0, 0, 0), B, d, h->cfg.max_len, 0, 1, st, s, 1));
-    for (int l = 0; l < h->cfg.n_layers[1]; ++l) SFB_TRY(block_step(h, 1, l, x1, s));
-    SFB_TRY(head(h, 1, x1, WS_<float>(h, h->buf.logits[1]), B, s));
+    SFB_TRY(group_step(h, 1, x1, WS_<float>(h, h->buf.logits[1]), s));
     p.logits = WS_<float>(h, h->buf.logits[1]); p.V = h->cfg.vocab[1]; p.tuple_i = 1;
     p.hist = h->hist ? h->hist + (int64_t)h->cfg.max_rows * h->cfg.max_steps * h->cfg.vocab[0] : nullptr;
     p.hist_row_stride = (int64_t)h->cfg.max_steps * h->cfg.vocab[1];
@@ -452,8 +586,7 @@ static int enqueue_step(sfb200_ar *h, const float *noise, cudaStream_t s) {
     SFB_TRY(launch_embed(h->tokens, W_(h, SFB200_W_TOK_EMB0, 0, 0), W_(h, SFB200_W_TOK_EMB1, 0, 0),
                          W_(h, SFB200_W_EXTRA_EMB, 0, 0), W_(h, SFB200_W_POS_EMB, 0, 0), W_(h, SFB200_W_COND_POS_EMB, 0, 0),
                          x0, B, d, h->cfg.max_len, 0, 1, 0, p.end0, st, s));
-    for (int l = 0; l < h->cfg.n_layers[0]; ++l) SFB_TRY(block_step(h, 0, l, x0, s));
-    SFB_TRY(head(h, 0, x0, WS_<float>(h, h->buf.logits[0]), B, s));
+    SFB_TRY(group_step(h, 0, x0, WS_<float>(h, h->buf.logits[0]), s));
     return SFB200_OK;
 }
 

@@ -697,6 +697,8 @@ struct SampleArgs {
     int64_t hist_row_stride;    // floats between rows of the history (= max_steps * V)
     int64_t noise_step_stride;  // floats between steps in the noise slab (= 4 * B * Vmax)
     int noise_row_stride;       // floats between rows of one noise draw (= Vmax)
+    float *logp;                // log-softmax(masked logits)[sampled token]: row b at logp + b*logp_row_stride + 2*step + tuple_i
+    int64_t logp_row_stride;    // (= 2 * max_steps), or logp == NULL
 };
 
 __global__ void __launch_bounds__(SMP_THREADS) ar_sample_kernel(SampleArgs a) {
@@ -740,21 +742,43 @@ __global__ void __launch_bounds__(SMP_THREADS) ar_sample_kernel(SampleArgs a) {
         }
         nxt = lo < L_cond ? row[2 * lo] : a.end0 + 1;
     }
+    auto masked = [&](int v) -> float {     // the masker's output for vocabulary entry v
+        float x = lg[v];
+        if (a.tuple_i == 1) {
+            if (val_forced) x = (v == a.end1) ? 1.0f : -INFINITY;
+        } else {
+            if (a.mask_invalid && step_j > 0 && v <= last && v != a.end0) x = -INFINITY;
+            if (a.mask_invalid_completion && v > nxt) x = -INFINITY;
+        }
+        return x;
+    };
+    float xmax = -INFINITY;
     for (int v = tid; v < npad; v += SMP_THREADS) {
         unsigned long long key = 0ull;
         if (v < V) {
-            float x = lg[v];
-            if (a.tuple_i == 1) {
-                if (val_forced) x = (v == a.end1) ? 1.0f : -INFINITY;
-            } else {
-                if (a.mask_invalid && step_j > 0 && v <= last && v != a.end0) x = -INFINITY;
-                if (a.mask_invalid_completion && v > nxt) x = -INFINITY;
-            }
+            const float x = masked(v);
+            xmax = fmaxf(xmax, x);
             if (hist) hist[v] = x;
             const float l = x / a.temperature;
             key = ((unsigned long long)float_order(l) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)v);
         }
         keys[v] = key;
+    }
+    // ---- log-sum-exp of the masked logits (for the sampled token's log-probability: compute_log_probs, shapeformer.py:407-418)
+    float lse = 0.f;
+    if (a.logp) {
+        xmax = warp_max(xmax);
+        if ((tid & 31) == 0) red_f[tid >> 5] = xmax;
+        __syncthreads();
+        xmax = warp_max(red_f[tid & 31]);
+        __syncthreads();
+        float se = 0.f;
+        for (int v = tid; v < V; v += SMP_THREADS) se += expf(masked(v) - xmax);   // -inf -> 0
+        se = warp_sum(se);
+        if ((tid & 31) == 0) red_f[tid >> 5] = se;
+        __syncthreads();
+        se = warp_sum(red_f[tid & 31]);
+        lse = xmax + logf(se);
     }
     __syncthreads();
 
@@ -968,7 +992,13 @@ __global__ void __launch_bounds__(SMP_THREADS) ar_sample_kernel(SampleArgs a) {
             const int ov = __shfl_xor_sync(0xffffffffu, best_v, o);
             if (ob > best || (ob == best && ov < best_v)) { best = ob; best_v = ov; }
         }
-        if (tid == 0) a.tokens[((size_t)b * a.max_len + L) * 2 + a.tuple_i] = (int64_t)best_v;
+        if (tid == 0) {
+            a.tokens[((size_t)b * a.max_len + L) * 2 + a.tuple_i] = (int64_t)best_v;
+            if (a.logp) {
+                const int step = a.st ? a.st[ST_STEPS] : 0;
+                a.logp[(size_t)b * a.logp_row_stride + 2 * step + a.tuple_i] = masked(best_v) - lse;
+            }
+        }
     }
 }
 
@@ -1065,6 +1095,7 @@ int launch_sample(const SampleLaunch &p, cudaStream_t s) {
     a.mask_invalid_completion = p.sp.mask_invalid_completion;
     a.st = p.st; a.hist_row_stride = p.hist_row_stride; a.noise_step_stride = p.noise_step_stride;
     a.noise_row_stride = p.noise_row_stride > 0 ? p.noise_row_stride : p.V;
+    a.logp = p.logp; a.logp_row_stride = p.logp_row_stride;
     // keys (8 B each) + the ev / compaction-list region (>= 1024 x 8 B)
     const size_t smem = (size_t)npad * 8 + ((size_t)npad * 4 > 8192 ? (size_t)npad * 4 : 8192);
     static unsigned long long attr_done = 0;   // bit per device

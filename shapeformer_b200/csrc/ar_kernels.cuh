@@ -17,6 +17,8 @@ struct SampleLaunch {
     const int32_t *st;
     int64_t hist_row_stride, noise_step_stride;
     int noise_row_stride;
+    float *logp = nullptr;          // (B, max_steps, 2) log-probability of every sampled token, or NULL
+    int64_t logp_row_stride = 0;
 };
 
 int launch_state_init(int32_t *st, int L_cond, cudaStream_t s);
@@ -42,8 +44,41 @@ int set_ps_timeline(unsigned long long *buf);
 int launch_tc_pretile(const float *W, float *Wt, int N, int K, cudaStream_t s);
 int launch_linear_tc_ps(const float *x, const float *Wt, const float *bias, const float *residual, float *y, int M, int N, int K,
                         int act, cudaStream_t stream);
+// ---- decode-step GEMM chain (ar_chain.cu): a list of nn.Linear phases run by ONE persistent kernel
+constexpr int CH_MAXP = 5;            // phases per launch
+constexpr int CH_MAX_BARRIERS = 15;   // grid barriers per launch; counters [0, CH_MAX_BARRIERS) + the exit counter
+struct alignas(64) TensorMapBlob { unsigned char b[128]; };   // a CUtensorMap (cuda.h) without the driver header
+struct ChainPhase {
+    const float *x;          // (M, K) input activations (GEMM phases)
+    const float *ln_g, *ln_b;   // LayerNorm weight / bias applied to x on load, or NULL
+    const float *stats_in;   // (M, ceil(K/512), 2) per-row (mean, M2) pieces of x when ln_g != NULL
+    const float *bias;       // (N) or NULL
+    const float *residual;   // (M, N) or NULL (may alias y)
+    float *y;                // (M, N) output, or NULL (statistics-only phase)
+    float *stats_out;        // (M, ceil(N/512), 2) pieces of the OUTPUT rows (a LayerNorm follows), or NULL
+    int N, K;
+    int tiles, splits;       // tiles = ceil(N/128); tiles * splits <= grid.  tiles == 0: no GEMM, the reduction step only sees
+                             // `residual` (used to produce stats_out for a row vector written by an earlier kernel)
+    int act;                 // 0 none, 1 exact-erf GELU
+    int wait_before;         // 1: x / stats_in are produced by an earlier phase of the same launch (grid barrier first)
+};
+struct ChainArgs {
+    TensorMapBlob wmap[CH_MAXP];   // weight tensor map of each GEMM phase (chain_weight_map)
+    ChainPhase ph[CH_MAXP];
+    int n_phases, M;
+    float *scratch;                // chain_scratch_floats(grid) floats: split-K partial tiles
+    unsigned int *bar;             // CH_MAX_BARRIERS + 1 counters, zero between launches
+};
+int chain_weight_map(const float *W, int N, int K, void *map_out /* TensorMapBlob */);
+int chain_grid_size();
+void chain_plan(int N, int K, int grid, int *tiles, int *splits);
+size_t chain_scratch_floats(int grid);
+int launch_chain(const ChainArgs &args, cudaStream_t stream);
+
 int launch_attn_decode(const float *qkv, float *kc, float *vc, float *out, float *part, int B, int H, int max_len, int pos,
                        const int32_t *st, int n_split, cudaStream_t s, int group = 1, int lcond = 0, int lcond_delta = 0);
+int launch_attn_grouped(const float *qkv, float *kc, float *vc, float *out, float *part, int *cnt, int B, int H, int max_len, int pos,
+                        const int32_t *st, int group, int lcond, int lcond_delta, cudaStream_t s);
 int launch_attn_prefill(const float *qkv, float *kc, float *vc, float *out, int B, int H, int T, int max_len,
                         cudaStream_t s, const int32_t *rowmap = nullptr);
 int launch_sample(const SampleLaunch &p, cudaStream_t s);

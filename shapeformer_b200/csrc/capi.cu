@@ -89,6 +89,36 @@ int sfb200_linear_tc_ps(const float *x, const float *Wt, const float *bias, cons
     if (!x || !Wt || !y || (act != 0 && act != 1)) return SFB200_E_ARG;
     return launch_linear_tc_ps(x, Wt, bias, residual, y, M, N, K, act, as_stream(stream));
 }
+// workspace of sfb200_chain_linear: [barrier counters 256 B | row statistics 64 x 8 pieces x 2 floats | split-K partials]
+static const int64_t kChainWsBar = 256, kChainWsStats = 64 * 8 * 2 * 4;
+int64_t sfb200_chain_workspace_bytes(void) { return kChainWsBar + kChainWsStats + (int64_t)chain_scratch_floats(160) * 4; }
+int sfb200_chain_linear(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
+                        int act, const float *ln_w, const float *ln_b, void *workspace, void *stream) {
+    if (!x || !W || !y || !workspace || (act != 0 && act != 1) || M < 1 || M > 64 || N < 1 || K < 32 || K % 32 != 0 || K > 4096)
+        return SFB200_E_ARG;
+    if ((ln_w == nullptr) != (ln_b == nullptr)) return SFB200_E_ARG;
+    int grid = chain_grid_size();
+    if (grid <= 0) return SFB200_E_CUDA;
+    if (grid > 160) grid = 160;
+    char *ws = static_cast<char *>(workspace);
+    float *stats = reinterpret_cast<float *>(ws + kChainWsBar);
+    ChainArgs a;
+    memset(&a, 0, sizeof(a));
+    a.M = M;
+    a.bar = reinterpret_cast<unsigned int *>(ws);
+    a.scratch = reinterpret_cast<float *>(ws + kChainWsBar + kChainWsStats);
+    if (ln_w) {   // statistics-only phase over the input rows, then the GEMM applies the LayerNorm on load
+        ChainPhase &s0 = a.ph[a.n_phases++];
+        s0.residual = x; s0.stats_out = stats; s0.N = K;
+    }
+    ChainPhase &ph = a.ph[a.n_phases];
+    SFB_TRY(chain_weight_map(W, N, K, &a.wmap[a.n_phases]));
+    a.n_phases++;
+    ph.x = x; ph.ln_g = ln_w; ph.ln_b = ln_b; ph.stats_in = ln_w ? stats : nullptr; ph.bias = bias; ph.residual = residual;
+    ph.y = y; ph.N = N; ph.K = K; ph.act = act; ph.wait_before = ln_w ? 1 : 0;
+    chain_plan(N, K, grid, &ph.tiles, &ph.splits);
+    return launch_chain(a, as_stream(stream));
+}
 int sfb200_debug_ps_timeline(void *buf16) { return set_ps_timeline(static_cast<unsigned long long *>(buf16)); }
 int sfb200_layernorm(const float *x, const float *w, const float *b, float *y, int rows, int d, void *stream) {
     if (!x || !w || !b || !y) return SFB200_E_ARG;
@@ -99,6 +129,13 @@ int sfb200_attn_decode(const float *qkv, float *kcache, float *vcache, float *ou
     if (!qkv || !kcache || !vcache || !out || B < 1 || H < 1 || pos < 0 || pos >= max_len) return SFB200_E_ARG;
     if (pos_dev) return SFB200_E_ARG;  // device-side position is an engine-internal mode (state words)
     return launch_attn_decode(qkv, kcache, vcache, out, part, B, H, max_len, pos, nullptr, n_split, as_stream(stream));
+}
+int sfb200_attn_decode_grouped(const float *qkv, float *kcache, float *vcache, float *out, float *part, int32_t *counters, int B,
+                               int H, int max_len, int pos, int group, int shared_len, void *stream) {
+    if (!qkv || !kcache || !vcache || !out || !part || !counters || B < 1 || H < 1 || pos < 0 || pos >= max_len) return SFB200_E_ARG;
+    if (shared_len < 0) return SFB200_E_ARG;
+    return launch_attn_grouped(qkv, kcache, vcache, out, part, counters, B, H, max_len, pos, nullptr, group, shared_len, 0,
+                               as_stream(stream));
 }
 int sfb200_attn_prefill(const float *qkv, float *kcache, float *vcache, float *out, int B, int H, int T, int max_len,
                         void *stream) {

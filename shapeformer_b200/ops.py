@@ -42,6 +42,29 @@ def linear_tc_ps(x, W, bias=None, residual=None, act=None):
     return y
 
 
+_chain_ws = {}
+
+
+def linear_chain(x, W, bias=None, residual=None, act=None, ln=None):
+    """y = act(LN?(x) @ W.T + bias) + residual for M <= 64 rows through the persistent GEMM-chain kernel the sampler's decode
+    step uses (fp32 weights streamed by TMA, 3xTF32 on tcgen05, split-K reduced through L2).  ln = (weight, bias) applies a
+    LayerNorm (eps 1e-5) to x on load.  `residual` may alias the returned tensor's role (in-place update is what the engine
+    does); here a fresh y is returned."""
+    lib = _lib.load()
+    M, K = x.shape
+    N = W.shape[0]
+    ws = _chain_ws.get(x.device)
+    if ws is None:
+        ws = torch.zeros(lib.sfb200_chain_workspace_bytes(), dtype=torch.uint8, device=x.device)
+        _chain_ws[x.device] = ws
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    _lib.check(lib.sfb200_chain_linear(_lib.ptr(x), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(residual), _lib.ptr(y), M, N, K,
+                                       1 if act == "gelu" else 0, _lib.ptr(ln[0]) if ln else None,
+                                       _lib.ptr(ln[1]) if ln else None, _lib.ptr(ws), _lib.stream_ptr()),
+               "sfb200_chain_linear")
+    return y
+
+
 def layernorm(x, w, b):
     lib = _lib.load()
     rows, d = x.shape
@@ -49,6 +72,23 @@ def layernorm(x, w, b):
     _lib.check(lib.sfb200_layernorm(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), rows, d, _lib.stream_ptr()),
                "sfb200_layernorm")
     return y
+
+
+def attn_decode_grouped(qkv, kcache, vcache, pos, group, shared_len):
+    """attn_decode for contiguous groups of `group` rows whose first `shared_len` cached positions are identical (read from
+    the group's first row).  Returns (B, d); caches updated in place at `pos`."""
+    lib = _lib.load()
+    B = qkv.shape[0]
+    _, H, max_len, hd = kcache.shape
+    assert hd == 64
+    out = torch.empty(B, H * 64, dtype=torch.float32, device=qkv.device)
+    part = torch.empty(B * H * 3 * 66, dtype=torch.float32, device=qkv.device)
+    cnt = torch.zeros(B * H, dtype=torch.int32, device=qkv.device)
+    _lib.check(lib.sfb200_attn_decode_grouped(_lib.ptr(qkv), _lib.ptr(kcache), _lib.ptr(vcache), _lib.ptr(out), _lib.ptr(part),
+                                              _lib.ptr(cnt), B, H, max_len, pos, group, shared_len, _lib.stream_ptr()),
+               "sfb200_attn_decode_grouped")
+    assert int(cnt.abs().sum()) == 0      # the arrival counters reset themselves
+    return out
 
 
 def attn_decode(qkv, kcache, vcache, pos, n_split=1):

@@ -42,6 +42,44 @@ def test_linear_in_place_residual_and_determinism(cuda):
         assert torch.equal(a, ops.linear(x, W, b, residual=r))   # cluster split-K sums in rank order: bitwise stable
 
 
+@pytest.mark.parametrize("M,N,K", [(64, 128, 64), (64, 1024, 1024), (16, 3072, 1024), (17, 4097, 1024), (33, 1024, 4096),
+                                   (64, 4096, 1024), (64, 4097, 1024), (9, 256, 128), (1, 1024, 1024), (3, 384, 128),
+                                   (64, 128, 512), (12, 512, 128)])
+@pytest.mark.parametrize("mode", ["plain", "bias_gelu", "bias_res", "ln_bias", "ln_plain"])
+def test_linear_chain(cuda, M, N, K, mode):
+    """The persistent GEMM-chain kernel of the decode step, one phase at a time: fp32-level accuracy against an fp64
+    reference, with the LayerNorm fused into the activation load (row statistics merged from 512-column pieces)."""
+    x, W, b, r = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05), rnd(N, seed=3), rnd(M, N, seed=4)
+    g, be = rnd(K, seed=5, scale=0.2) + 1, rnd(K, seed=6, scale=0.1)
+    xd, Wd = x.double(), W.double()
+    if mode == "plain":
+        ref = xd @ Wd.t()
+        out = ops.linear_chain(x.to(cuda), W.to(cuda))
+    elif mode == "bias_gelu":
+        ref = F.gelu(xd @ Wd.t() + b.double())
+        out = ops.linear_chain(x.to(cuda), W.to(cuda), b.to(cuda), act="gelu")
+    elif mode == "bias_res":
+        ref = r.double() + xd @ Wd.t() + b.double()
+        out = ops.linear_chain(x.to(cuda), W.to(cuda), b.to(cuda), residual=r.to(cuda))
+    else:
+        xs = x * 3.0 + 0.5          # non-trivial mean / variance
+        h = F.layer_norm(xs.double(), (K,), g.double(), be.double(), 1e-5)
+        ref = h @ Wd.t() + (b.double() if mode == "ln_bias" else 0.0)
+        out = ops.linear_chain(xs.to(cuda), W.to(cuda), b.to(cuda) if mode == "ln_bias" else None, ln=(g.to(cuda), be.to(cuda)))
+    err = (out.cpu().double() - ref).abs().max().item()
+    scale = max(1.0, ref.abs().max().item())
+    assert err < 2.5e-6 * scale * max(1.0, (K / 1024) ** 0.5), (err, scale)   # single-pass TF32 would be ~1e-3
+
+
+def test_linear_chain_deterministic_and_repeatable(cuda):
+    """Split-K partials are reduced through L2 in split order: bitwise stable; the barrier counters reset themselves."""
+    x, W, b = rnd(64, 1024, seed=1).to(cuda), rnd(1024, 1024, seed=2, scale=0.03).to(cuda), rnd(1024, seed=3).to(cuda)
+    r = rnd(64, 1024, seed=4).to(cuda)
+    a = ops.linear_chain(x, W, b, residual=r)
+    for _ in range(20):
+        assert torch.equal(a, ops.linear_chain(x, W, b, residual=r))
+
+
 @pytest.mark.parametrize("rows,d", [(1, 128), (64, 1024), (777, 1024)])
 def test_layernorm(cuda, rows, d):
     x, w, b = rnd(rows, d, seed=1, scale=3.0) + 0.5, rnd(d, seed=2) + 1, rnd(d, seed=3)
@@ -53,6 +91,31 @@ def _ref_attn(q, K, V):
     """q (B,H,hd), K/V (B,H,T,hd) -> (B,H*hd) exactly as CausalSelfAttention for the newest query."""
     att = (q[:, :, None] @ K.transpose(-2, -1)) * (1.0 / math.sqrt(q.shape[-1]))
     return (F.softmax(att, -1) @ V)[:, :, 0].reshape(q.shape[0], -1)
+
+
+@pytest.mark.parametrize("B,H,G,shared,pos", [(4, 2, 4, 0, 0), (4, 2, 4, 5, 5), (8, 16, 4, 256, 511), (6, 3, 2, 33, 40),
+                                               (8, 2, 8, 17, 100), (12, 4, 6, 31, 32), (64, 16, 4, 256, 300), (4, 2, 2, 100, 60)])
+def test_attn_decode_grouped(cuda, B, H, G, shared, pos):
+    """Grouped decode attention (shared prefix scored once per group from the leader's cache rows, TMA-staged tiles, partial
+    states merged by the last arriver) against torch fp32 on the full per-row caches; appends the new K/V."""
+    max_len, d = 520, H * 64
+    qkv = rnd(B, 3 * d, seed=1)
+    Kc, Vc = rnd(B, H, max_len, 64, seed=2), rnd(B, H, max_len, 64, seed=3)
+    sh = min(shared, pos)
+    lead = (torch.arange(B) // G) * G
+    Kc[:, :, :sh] = Kc[lead][:, :, :sh]        # the group's rows hold identical prefix K/V
+    Vc[:, :, :sh] = Vc[lead][:, :, :sh]
+    kc, vc = Kc.to(cuda), Vc.to(cuda)
+    # poison the siblings' prefix copies: the kernel must read the LEADER's rows only
+    sib = torch.arange(B) % G != 0
+    kc[sib.to(cuda), :, :sh] = float("nan")
+    out = ops.attn_decode_grouped(qkv.to(cuda), kc, vc, pos, G, shared).cpu()
+    q, k, v = (qkv[:, i * d:(i + 1) * d].view(B, H, 64) for i in range(3))
+    Kr, Vr = Kc.clone(), Vc.clone()
+    Kr[:, :, pos], Vr[:, :, pos] = k, v
+    ref = _ref_attn(q, Kr[:, :, :pos + 1], Vr[:, :, :pos + 1])
+    assert (out - ref).abs().max() < 2e-5
+    assert torch.equal(kc[:, :, pos].cpu(), k) and torch.equal(vc[:, :, pos].cpu(), v)
 
 
 @pytest.mark.parametrize("B,H,pos,n_split", [(1, 2, 0, 1), (3, 2, 1, 1), (2, 16, 7, 1), (2, 4, 100, 3), (1, 16, 511, 8),
