@@ -3,18 +3,18 @@
 // replacing one launch per GEMM / LayerNorm (Block.forward, transformer/mingpt.py:108-111; heads :222-231).
 //
 // One CTA per SM (grid = SM count, all co-resident), warp-specialised, decoupled through mbarriers:
-//   warp 9  (loader)  : streams the fp32 weight tiles (128 output features x 32 k, 16 KB) of EVERY phase of the launch through
+//   warp 13 (loader)  : streams the fp32 weight tiles (128 output features x 32 k, 16 KB) of EVERY phase of the launch through
 //                       a 10-deep shared-memory ring with TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B tensor maps over the
 //                       row-major fp32 weights) — weights are constants, so the stream never waits for a phase boundary and
 //                       runs through the grid barriers; the fp32 blob is read exactly once per step (no pre-split copy);
 //   warps 0-3 (W split): thread = one weight row: conflict-free read of its 128-byte swizzled row, hi = rna_tf32(w),
 //                       lo = rna_tf32(w - hi), tcgen05.st of hi|lo into a 4-deep TENSOR-MEMORY ring (the A operand lives in
 //                       TMEM); may run up to 4 chunks ahead of the activations, i.e. into the next phase;
-//   warps 4-7 (X)     : activation operand: coherent loads of x[64 x 32] from L2, optional LayerNorm applied on the fly from
+//   warps 4-11 (X)    : activation operand: coherent loads of x[64 x 32] from L2, optional LayerNorm applied on the fly from
 //                       per-row statistics, TF32 hi/lo split into UMMA-layout shared tiles; promotion of the TMEM accumulator
 //                       into fp32 registers every 2 chunks (the tensor-core accumulator is not round-to-nearest: chains stay
 //                       at 24 MMAs); split-K partial tile -> L2 scratch; grid barrier; distributed reduction;
-//   warp 8  (MMA)     : 12 tcgen05.mma.kind::tf32 per chunk (lo*hi + hi*lo + hi*hi), swap-AB: UMMA M = 128 output features,
+//   warp 12 (MMA)     : 12 tcgen05.mma.kind::tf32 per chunk (lo*hi + hi*lo + hi*hi), swap-AB: UMMA M = 128 output features,
 //                       UMMA N = 64 activation rows.
 // Split-K across CTAs (tiles x splits <= grid) is reduced THROUGH L2 in a fixed order (deterministic): every (tile, split)
 // unit stores its 64 x 128 partial, one grid barrier, then each CTA finalises (row, 512-column) items: sum over the splits in
@@ -29,7 +29,8 @@ namespace sfb {
 
 using namespace tc;
 
-constexpr int CH_THREADS = 320;
+constexpr int CH_THREADS = 448;            // warps 0-3 W split, 4-11 X (two per TMEM lane quadrant), 12 MMA issuer, 13 TMA loader
+constexpr int CH_XT = 256;                 // X threads
 constexpr int CH_WS = 10;                    // raw weight stages
 constexpr int CH_XS = 3;                     // activation hi/lo stages
 constexpr int CH_AS = 4;                     // TMEM A-operand stages
@@ -40,8 +41,9 @@ constexpr int CH_X_TILE = CH_BN * 32 * 4;    // 8 KB
 constexpr int CH_OFF_W = 0;
 constexpr int CH_OFF_XH = CH_OFF_W + CH_WS * CH_W_TILE;
 constexpr int CH_OFF_XL = CH_OFF_XH + CH_XS * CH_X_TILE;
-constexpr int CH_OFF_BAR = CH_OFF_XL + CH_XS * CH_X_TILE;       // mbarriers (<= 256 B)
-constexpr int CH_OFF_STAT = CH_OFF_BAR + 256;                   // mean[64] rstd[64] red[16]
+constexpr int CH_N_MBAR = 2 * CH_WS + 2 * CH_AS + 2 * CH_XS + 4;    // mbarriers
+constexpr int CH_OFF_BAR = CH_OFF_XL + CH_XS * CH_X_TILE;
+constexpr int CH_OFF_STAT = CH_OFF_BAR + ((CH_N_MBAR * 8 + 8 + 127) / 128) * 128;   // (+ the TMEM address slot)                   // mean[64] rstd[64] red[16]
 constexpr int CH_SMEM = CH_OFF_STAT + (64 + 64 + 16) * 4 + 64;
 constexpr int CH_COL_D = 0, CH_COL_A = 2 * CH_BN;               // TMEM columns: D0 | D1 | A ring (AS x (hi 32 | lo 32))
 constexpr int CH_ITEM_COLS = 512;                               // columns per reduction item = per LayerNorm statistics piece
@@ -65,9 +67,9 @@ __device__ __forceinline__ void mbar_expect_tx_ch(uint64_t *bar, uint32_t bytes)
 }
 __device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
 
-// ---- grid barrier among the X warps' leaders (128 X threads per CTA take part; all other warps are decoupled by mbarriers)
+// ---- grid barrier among the X warps' leaders (the 256 X threads of every CTA take part; all other warps are decoupled by mbarriers)
 __device__ __forceinline__ void chain_grid_barrier(unsigned int *ctr, unsigned int n_cta, int xt) {
-    bar_sync(2, 128);
+    bar_sync(2, CH_XT);
     if (xt == 0) {
         __threadfence();
         atomicAdd(ctr, 1u);
@@ -77,19 +79,19 @@ __device__ __forceinline__ void chain_grid_barrier(unsigned int *ctr, unsigned i
         } while (v < n_cta);
         __threadfence();
     }
-    bar_sync(2, 128);
+    bar_sync(2, CH_XT);
 }
 
-// sum over the 128 X threads (4 warps), result broadcast; `red` = 8 floats of shared memory
+// sum over the first 128 X threads (4 warps), result broadcast; `red` = 8 floats of shared memory
 __device__ __forceinline__ float x_block_sum(float v, float *red, int xt) {
     v = warp_sum(v);
-    bar_sync(3, 128);                 // previous use of `red` is over
+    bar_sync(4, 128);                 // previous use of `red` is over
     if ((xt & 31) == 0) red[xt >> 5] = v;
-    bar_sync(3, 128);
+    bar_sync(4, 128);
     return (red[0] + red[1]) + (red[2] + red[3]);
 }
 
-__global__ void __maxnreg__(200) ar_chain_kernel(const __grid_constant__ ChainArgs a) {
+__global__ void __launch_bounds__(CH_THREADS, 1) ar_chain_kernel(const __grid_constant__ ChainArgs a) {
     pdl_trigger();
     extern __shared__ __align__(1024) unsigned char ch_smem[];
     unsigned char *smem = ch_smem;
@@ -110,11 +112,11 @@ __global__ void __maxnreg__(200) ar_chain_kernel(const __grid_constant__ ChainAr
     if (tid == 0) {
         for (int i = 0; i < CH_WS; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wfree[i], 128); }
         for (int i = 0; i < CH_AS; ++i) { mbar_init(&afull[i], 128); mbar_init(&afree[i], 1); }
-        for (int i = 0; i < CH_XS; ++i) { mbar_init(&xfull[i], 128); mbar_init(&xfree[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&dfull[i], 1); mbar_init(&dfree[i], 128); }
+        for (int i = 0; i < CH_XS; ++i) { mbar_init(&xfull[i], CH_XT); mbar_init(&xfree[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&dfull[i], 1); mbar_init(&dfree[i], CH_XT); }
         mbar_fence_init();
     }
-    if (warp == 8) tmem_alloc<512>(tmem_slot);
+    if (warp == 12) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -131,7 +133,7 @@ __global__ void __maxnreg__(200) ar_chain_kernel(const __grid_constant__ ChainAr
         return c_end > c_beg;
     };
 
-    if (warp == 9) {
+    if (warp == 13) {
         // ================================ weight loader (TMA), free-running across phases ================================
         if (lane == 0) {
             for (int p = 0; p < a.n_phases; ++p)
@@ -181,7 +183,7 @@ __global__ void __maxnreg__(200) ar_chain_kernel(const __grid_constant__ ChainAr
                 mbar_arrive(&afull[sa]);
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == 12) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
             constexpr uint32_t IDESC = instr_desc(2, 128, CH_BN);
@@ -216,8 +218,10 @@ __global__ void __maxnreg__(200) ar_chain_kernel(const __grid_constant__ ChainAr
         __syncwarp();
     } else {
         // ================================ X warps: activations, promotion, partials, barriers, reduction ================================
-        const int xt = tid - 128;                                   // 0..127
+        const int xt = tid - 128;                                   // 0..255
+        const int row = xt & 127, half = xt >> 7;                   // TMEM lane (weight row of the tile) / which 32 D columns
         const uint32_t lane_off = (uint32_t)(32 * (warp & 3)) << 16;
+        constexpr int HB = CH_BN / 2;
         const int M = a.M;
         pdl_wait();                                                 // everything below touches data of earlier kernels
         uint32_t it = 0, gg = 0;
@@ -248,38 +252,37 @@ __global__ void __maxnreg__(200) ar_chain_kernel(const __grid_constant__ ChainAr
                         }
                         s_mean[xt] = mean; s_rstd[xt] = rstd;
                     }
-                    bar_sync(3, 128);
+                    bar_sync(3, CH_XT);
                 }
-                float acc[CH_BN];
+                float acc[HB];             // acc[j] = D[row][half * 32 + j]
 #pragma unroll
-                for (int j = 0; j < CH_BN; ++j) acc[j] = 0.f;
+                for (int j = 0; j < HB; ++j) acc[j] = 0.f;
                 auto drain = [&]() {          // acc += D[gg & 1]; advances gg
                     const uint32_t b = gg & 1;
                     mbar_wait(&dfull[b], (gg >> 1) & 1);
                     tc_fence_after();
-#pragma unroll
-                    for (int h = 0; h < CH_BN / 32; ++h) {
+                    {
                         uint32_t v[32];
-                        tmem_ld32(tmem_base + lane_off + CH_COL_D + b * CH_BN + h * 32, v);
+                        tmem_ld32(tmem_base + lane_off + CH_COL_D + b * CH_BN + half * HB, v);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[h * 32 + j] += __uint_as_float(v[j]);
+                        for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(v[j]);
                     }
                     tc_fence_before();
                     mbar_arrive(&dfree[b]);
                     ++gg;
                 };
-                // thread -> 4 float4 of the 64 x 32 chunk: element idx = xt + 128 j: row = idx >> 3, 16-byte chunk = idx & 7
-                auto load_x = [&](int c, float4 (&v)[4]) {
+                // thread -> 2 float4 of the 64 x 32 chunk: element idx = xt + 256 j: row = idx >> 3, 16-byte chunk = idx & 7
+                auto load_x = [&](int c, float4 (&v)[2]) {
                     const int k0 = c * 32;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int idx = xt + 128 * j, r = idx >> 3, chk = idx & 7;
+                    for (int j = 0; j < 2; ++j) {
+                        const int idx = xt + CH_XT * j, r = idx >> 3, chk = idx & 7;
                         v[j] = r < M ? ldcg4(ph.x + (size_t)r * K + k0 + chk * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 };
                 const int nch = c_end - c_beg;
-                float4 cur[4], nxt[4];
+                float4 cur[2], nxt[2];
                 load_x(c_beg, cur);
                 int pending = 0;              // promotion groups committed by the MMA warp but not drained yet
                 for (int i = 0; i < nch; ++i, ++it) {
@@ -290,8 +293,8 @@ __global__ void __maxnreg__(200) ar_chain_kernel(const __grid_constant__ ChainAr
                     float *xl = reinterpret_cast<float *>(smem + CH_OFF_XL + sx * CH_X_TILE);
                     const int k0 = (c_beg + i) * 32;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int idx = xt + 128 * j, r = idx >> 3, chk = idx & 7;
+                    for (int j = 0; j < 2; ++j) {
+                        const int idx = xt + CH_XT * j, r = idx >> 3, chk = idx & 7;
                         float4 v = cur[j];
                         if (ph.ln_g && r < M) {
                             const float mean = s_mean[r], rstd = s_rstd[r];
@@ -317,18 +320,18 @@ __global__ void __maxnreg__(200) ar_chain_kernel(const __grid_constant__ ChainAr
                         ++pending;
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+                    for (int j = 0; j < 2; ++j) cur[j] = nxt[j];
                 }
                 while (pending > 0) { drain(); --pending; }
                 // ---- partial tile of this (tile, split) unit -> L2 scratch [unit][m][128]
-                float *part = a.scratch + ((size_t)cta * CH_BN) * 128 + xt;
+                float *part = a.scratch + ((size_t)cta * CH_BN + half * HB) * 128 + row;
 #pragma unroll
-                for (int j = 0; j < CH_BN; ++j)
-                    if (j < M) __stcg(part + j * 128, acc[j]);
+                for (int j = 0; j < HB; ++j)
+                    if (half * HB + j < M) __stcg(part + j * 128, acc[j]);
             }
             if (ph.tiles > 0) { chain_grid_barrier(a.bar + bar_i, n_cta, xt); ++bar_i; }
-            // ---- distributed reduction: items (row m, 512-column block cb)
-            {
+            // ---- distributed reduction: items (row m, 512-column block cb), by the first 128 X threads
+            if (xt < 128) {
                 const int N = ph.N, S = ph.tiles > 0 ? ph.splits : 0;
                 const int CB = (N + CH_ITEM_COLS - 1) / CH_ITEM_COLS;
                 const bool vec = (N & 3) == 0;
@@ -384,7 +387,7 @@ __global__ void __maxnreg__(200) ar_chain_kernel(const __grid_constant__ ChainAr
             }
         }
         // ---- reset the barrier counters for the next launch: the last CTA to get here knows everybody passed every barrier
-        bar_sync(2, 128);
+        bar_sync(2, CH_XT);
         if (xt == 0) {
             __threadfence();
             const unsigned int old = atomicAdd(a.bar + CH_MAX_BARRIERS, 1u);
@@ -396,7 +399,7 @@ __global__ void __maxnreg__(200) ar_chain_kernel(const __grid_constant__ ChainAr
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 12) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
