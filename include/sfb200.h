@@ -224,6 +224,12 @@ int64_t sfb200_chain_workspace_bytes(void);
 int sfb200_chain_linear(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
                         int act, const float *ln_w, const float *ln_b, void *workspace, void *stream);
 
+/* Development aid: register a device buffer of 128 uint64 (or NULL to stop).  CTA 0 of every GEMM-chain launch adds the
+ * nanoseconds spent in each stage of each phase to slot [phase * 8 + stage] and the visit count to slot [64 + phase * 8 +
+ * stage] (stages: 0 wait-before barrier, 1 row statistics, 2 operand prefetch issue, 3 chunk loop, 4 partial store, 5 post-GEMM
+ * barrier, 6 reduction; slot 62 = entry -> dependency wait).  The caller zeroes and reads the buffer. */
+int sfb200_debug_chain_timeline(void *buf128);
+
 /* Development aid: register a device buffer of 16 uint64; CTA (0,0) of sfb200_linear_tc_ps stamps %globaltimer (ns) at its
  * phase boundaries (slots documented in tc_gemm_ps.cu).  NULL unregisters. */
 int sfb200_debug_ps_timeline(void *buf16);

@@ -15,8 +15,7 @@ for (M, N, K) in [(33, 1024, 4096), (64, 1024, 2048), (4, 256, 1536), (64, 128, 
     print(M, N, K, 'nan rows', nan.any(1).nonzero().flatten().tolist()[:20], 'nan cols', int(nan.any(0).sum()),
           'err', (out.double() - ref)[~nan].abs().max().item())
     ws = ops._chain_ws[cuda]
-    st = ws[256:256 + 4096].view(torch.float32).view(64, -1)[:, :].cpu()
-    pieces = (K + 511) // 512
+        pieces = (K + 127) // 128
     stv = ws[256:256 + M * pieces * 8].view(torch.float32).view(M, pieces, 2).cpu()
     xm = xs.view(M, pieces, -1)
     print('  mean err', (stv[..., 0] - xm.mean(-1)).abs().max().item(), 'M2 err', (stv[..., 1] - ((xm - xm.mean(-1, keepdim=True)) ** 2).sum(-1)).abs().max().item(), 'nan stats', int(torch.isnan(stv).sum()))

@@ -75,6 +75,7 @@ SIGNATURES = {
     "sfb200_chain_workspace_bytes": (ctypes.c_int64, []),
     "sfb200_chain_linear": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp,
                                            vp, vp]),
+    "sfb200_debug_chain_timeline": (ctypes.c_int, [vp]),
     "sfb200_debug_ps_timeline": (ctypes.c_int, [vp]),
     "sfb200_layernorm": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp]),
     "sfb200_attn_decode": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,

@@ -30,8 +30,11 @@ namespace sfb {
 using namespace tc;
 
 constexpr int CH_THREADS = 448;            // warps 0-3 W split, 4-11 X (two per TMEM lane quadrant), 12 MMA issuer, 13 TMA loader
-constexpr int CH_XT = 256;                 // X threads
-constexpr int CH_WS = 10;                    // raw weight stages
+constexpr int CH_XT = 256;                   // X threads
+constexpr int CH_WS = 6;                     // raw weight stages
+constexpr int CH_XR = 8;                     // activation prefetch depth (chunks), thread-private staging in shared memory
+constexpr int CH_XRL = CH_XR / 2;            // ... per X group (the two groups convert alternate chunks)
+constexpr int CH_LNP = 2;                    // LayerNorm-fed GEMM phases per launch whose gamma / beta slices are staged
 constexpr int CH_XS = 3;                     // activation hi/lo stages
 constexpr int CH_AS = 4;                     // TMEM A-operand stages
 constexpr int CH_G = 2;                      // chunks per promotion group
@@ -43,10 +46,14 @@ constexpr int CH_OFF_XH = CH_OFF_W + CH_WS * CH_W_TILE;
 constexpr int CH_OFF_XL = CH_OFF_XH + CH_XS * CH_X_TILE;
 constexpr int CH_N_MBAR = 2 * CH_WS + 2 * CH_AS + 2 * CH_XS + 4;    // mbarriers
 constexpr int CH_OFF_BAR = CH_OFF_XL + CH_XS * CH_X_TILE;
-constexpr int CH_OFF_STAT = CH_OFF_BAR + ((CH_N_MBAR * 8 + 8 + 127) / 128) * 128;   // (+ the TMEM address slot)                   // mean[64] rstd[64] red[16]
-constexpr int CH_SMEM = CH_OFF_STAT + (64 + 64 + 16) * 4 + 64;
+constexpr int CH_OFF_STAT = CH_OFF_BAR + ((CH_N_MBAR * 8 + 8 + 127) / 128) * 128;   // (+ the TMEM address slot)   mean[64] rstd[64] red[16]
+constexpr int CH_OFF_XRAW = CH_OFF_STAT + 640;                  // [XR][2][256 threads] float4: per-thread activation prefetch
+constexpr int CH_OFF_LN = CH_OFF_XRAW + CH_XR * 2 * CH_XT * 16; // [LNP][gamma | beta][XR chunks][32] floats
+constexpr int CH_OFF_STST = CH_OFF_LN + CH_LNP * 2 * CH_XR * 32 * 4;   // [64 rows][8 pieces] float2: statistics staging
+constexpr int CH_SMEM = CH_OFF_STST + 64 * 8 * 8;
 constexpr int CH_COL_D = 0, CH_COL_A = 2 * CH_BN;               // TMEM columns: D0 | D1 | A ring (AS x (hi 32 | lo 32))
-constexpr int CH_ITEM_COLS = 512;                               // columns per reduction item = per LayerNorm statistics piece
+constexpr int CH_ITEM_COLS = 512;                               // columns per reduction item (128 threads x float4)
+constexpr int CH_STAT_COLS = 128;                               // columns per LayerNorm statistics piece (one warp)
 
 static_assert(CH_SMEM <= 232448, "chain kernel shared memory exceeds the 227 KB limit");
 static_assert(CH_COL_A + CH_AS * 64 <= 512, "TMEM columns");
@@ -67,28 +74,62 @@ __device__ __forceinline__ void mbar_expect_tx_ch(uint64_t *bar, uint32_t bytes)
 }
 __device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
 
+// Optional timeline probe (development aid): when a buffer is registered (sfb200_debug_chain_timeline), thread xt == 0 of
+// CTA 0 adds the SM cycles (clock64) since the previous stamp to slot [phase * 8 + stage] and counts the visits:
+// stages 0 wait_before barrier, 1 row statistics, 2 operand prefetch issued, 3 chunk loop + final promotion, 4 partial store,
+// 5 post-GEMM barrier, 6 reduction; slot 62 = kernel entry -> dependency wait done, 63 = launches.
+__device__ unsigned long long *g_chain_timeline = nullptr;
+#ifndef SFB_CHAIN_PROBE
+#define SFB_CHAIN_PROBE 0      // build with -DSFB_CHAIN_PROBE=1 for the timeline (costs registers and ~10 % of the kernel time)
+#endif
+#if SFB_CHAIN_PROBE
+struct ChainProbe {     // accumulates in (thread-local) memory, flushed to the global buffer once at the end
+    unsigned long long t;
+    unsigned int acc[64], cnt[64];
+    bool on;
+    __device__ __forceinline__ void start(bool enable) {
+        on = enable && g_chain_timeline != nullptr;
+        if (on) {
+            for (int i = 0; i < 64; ++i) { acc[i] = 0; cnt[i] = 0; }
+            t = clock64();
+        }
+    }
+    __device__ __forceinline__ void stamp(int slot) {
+        if (on) {
+            const unsigned long long now = clock64();      // SM cycles (the probing thread stays on one SM)
+            acc[slot] += (unsigned int)(now - t);
+            cnt[slot] += 1;
+            t = now;
+        }
+    }
+    __device__ __forceinline__ void flush() {
+        if (on)
+            for (int i = 0; i < 64; ++i)
+                if (cnt[i]) {
+                    atomicAdd(&g_chain_timeline[i], (unsigned long long)acc[i]);
+                    atomicAdd(&g_chain_timeline[64 + i], (unsigned long long)cnt[i]);
+                }
+    }
+};
+#else
+struct ChainProbe {
+    __device__ __forceinline__ void start(bool) {}
+    __device__ __forceinline__ void stamp(int) {}
+    __device__ __forceinline__ void flush() {}
+};
+#endif
+
 // ---- grid barrier among the X warps' leaders (the 256 X threads of every CTA take part; all other warps are decoupled by mbarriers)
 __device__ __forceinline__ void chain_grid_barrier(unsigned int *ctr, unsigned int n_cta, int xt) {
-    bar_sync(2, CH_XT);
+    bar_sync(2, CH_XT);          // every X thread's global writes happen-before the leader's release (cumulativity)
     if (xt == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(ctr) : "memory");
         unsigned int v;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(ctr) : "memory");
         } while (v < n_cta);
-        __threadfence();
     }
     bar_sync(2, CH_XT);
-}
-
-// sum over the first 128 X threads (4 warps), result broadcast; `red` = 8 floats of shared memory
-__device__ __forceinline__ float x_block_sum(float v, float *red, int xt) {
-    v = warp_sum(v);
-    bar_sync(4, 128);                 // previous use of `red` is over
-    if ((xt & 31) == 0) red[xt >> 5] = v;
-    bar_sync(4, 128);
-    return (red[0] + red[1]) + (red[2] + red[3]);
 }
 
 __global__ void __launch_bounds__(CH_THREADS, 1) ar_chain_kernel(const __grid_constant__ ChainArgs a) {
@@ -104,16 +145,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1) ar_chain_kernel(const __grid_co
     uint64_t *dfull = xfree + CH_XS;                                     // [2]  promotion group finished in D[b]
     uint64_t *dfree = dfull + 2;                                         // [2]  D[b] drained
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(dfree + 2);
-    float *s_mean = reinterpret_cast<float *>(smem + CH_OFF_STAT), *s_rstd = s_mean + 64, *s_red = s_rstd + 64;
+    float *s_mean = reinterpret_cast<float *>(smem + CH_OFF_STAT), *s_rstd = s_mean + 64;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cta = blockIdx.x, n_cta = gridDim.x;
 
     if (tid == 0) {
-        for (int i = 0; i < CH_WS; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wfree[i], 128); }
-        for (int i = 0; i < CH_AS; ++i) { mbar_init(&afull[i], 128); mbar_init(&afree[i], 1); }
-        for (int i = 0; i < CH_XS; ++i) { mbar_init(&xfull[i], CH_XT); mbar_init(&xfree[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&dfull[i], 1); mbar_init(&dfree[i], CH_XT); }
+        for (int i = 0; i < CH_WS; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wfree[i], 4); }
+        for (int i = 0; i < CH_AS; ++i) { mbar_init(&afull[i], 4); mbar_init(&afree[i], 1); }
+        for (int i = 0; i < CH_XS; ++i) { mbar_init(&xfull[i], CH_XT / 64); mbar_init(&xfree[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&dfull[i], 1); mbar_init(&dfree[i], CH_XT / 32); }
         mbar_fence_init();
     }
     if (warp == 12) tmem_alloc<512>(tmem_slot);
@@ -156,39 +197,55 @@ __global__ void __launch_bounds__(CH_THREADS, 1) ar_chain_kernel(const __grid_co
         const uint32_t lane_off = (uint32_t)(32 * warp) << 16;
         const int row = tid;   // weight row inside the tile == TMEM lane
         uint32_t it = 0;
+        ChainProbe wp;
+        wp.start(cta == 0 && tid == 0);
         for (int p = 0; p < a.n_phases; ++p) {
             int tile, c_beg, c_end;
             if (!unit_of(p, tile, c_beg, c_end)) continue;
             for (int c = c_beg; c < c_end; ++c, ++it) {
                 const uint32_t s = it % CH_WS, sa = it % CH_AS;
+                wp.stamp(43);
                 mbar_wait(&wfull[s], (it / CH_WS) & 1);
+                wp.stamp(40);
                 const float *wrow = reinterpret_cast<const float *>(smem + CH_OFF_W + s * CH_W_TILE) + row * 32;
+                // hi = the raw fp32 bits: the tensor core reads only the upper 19 bits of a tf32 operand, i.e. it truncates
+                // (hi_t = trunc_tf32(w), no instruction needed); lo = rna_tf32(w - hi_t), the subtraction being exact
                 uint32_t hi[32], lo[32];
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
                     const float4 v = ld4(wrow + ((ch ^ (row & 7)) << 2));
-                    split_tf32(v.x, hi[4 * ch + 0], lo[4 * ch + 0]);
-                    split_tf32(v.y, hi[4 * ch + 1], lo[4 * ch + 1]);
-                    split_tf32(v.z, hi[4 * ch + 2], lo[4 * ch + 2]);
-                    split_tf32(v.w, hi[4 * ch + 3], lo[4 * ch + 3]);
+                    hi[4 * ch + 0] = __float_as_uint(v.x); hi[4 * ch + 1] = __float_as_uint(v.y);
+                    hi[4 * ch + 2] = __float_as_uint(v.z); hi[4 * ch + 3] = __float_as_uint(v.w);
                 }
-                mbar_arrive(&wfree[s]);                      // the row is in registers: the raw stage may be refilled
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&wfree[s]);       // the rows are in registers: the raw stage may be refilled
+                wp.stamp(41);
                 if (it >= CH_AS) mbar_wait(&afree[sa], ((it / CH_AS) - 1) & 1);
+                wp.stamp(42);
                 tc_fence_after();
                 const uint32_t a_col = tmem_base + lane_off + CH_COL_A + sa * 64;
                 tmem_st32(a_col, hi);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float w = __uint_as_float(hi[i]);
+                    lo[i] = __float_as_uint(w - __uint_as_float(hi[i] & 0xFFFFE000u)) + 0x1000u;   // low 13 bits ignored by the MMA
+                }
                 tmem_st32(a_col + 32, lo);
                 tmem_st_wait();
                 tc_fence_before();
-                mbar_arrive(&afull[sa]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&afull[sa]);      // one arrival per warp: 4 instead of 128 shared-memory atomics
             }
         }
+        wp.flush();
     } else if (warp == 12) {
-        // ================================ MMA issuer ================================
-        if (lane == 0) {
+        // ================================ MMA issuer (whole warp converged; one elected lane issues) ================================
+        {
             constexpr uint32_t IDESC = instr_desc(2, 128, CH_BN);
             const uint32_t xh0 = smem_u32(smem + CH_OFF_XH), xl0 = smem_u32(smem + CH_OFF_XL);
             uint32_t it = 0, gg = 0;
+            ChainProbe mp;
+            mp.start(cta == 0 && lane == 0);
             for (int p = 0; p < a.n_phases; ++p) {
                 int tile, c_beg, c_end;
                 if (!unit_of(p, tile, c_beg, c_end)) continue;
@@ -196,26 +253,35 @@ __global__ void __launch_bounds__(CH_THREADS, 1) ar_chain_kernel(const __grid_co
                 for (int i = 0; i < nch; ++i, ++it) {
                     const uint32_t sa = it % CH_AS, sx = it % CH_XS, b = gg & 1;
                     const bool first = (i % CH_G) == 0;
+                    const bool last = (i % CH_G) == CH_G - 1 || i == nch - 1;
+                    mp.stamp(47);
                     if (first && gg >= 2) mbar_wait(&dfree[b], ((gg >> 1) - 1) & 1);
-                    mbar_wait(&afull[sa], (it / CH_AS) & 1);
+                    mp.stamp(44);
                     mbar_wait(&xfull[sx], (it / CH_XS) & 1);
+                    mp.stamp(46);
+                    mbar_wait(&afull[sa], (it / CH_AS) & 1);
+                    mp.stamp(45);
                     tc_fence_after();
                     const uint32_t d = tmem_base + CH_COL_D + b * CH_BN;
                     const uint32_t a_hi = tmem_base + CH_COL_A + sa * 64, a_lo = a_hi + 32;
                     const uint64_t bh = smem_desc_k128(xh0 + sx * CH_X_TILE), bl = smem_desc_k128(xl0 + sx * CH_X_TILE);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        mma_tf32_ts(d, a_lo + 8 * k, bh + 2 * k, IDESC, !(first && k == 0));
-                        mma_tf32_ts(d, a_hi + 8 * k, bl + 2 * k, IDESC, 1);
-                        mma_tf32_ts(d, a_hi + 8 * k, bh + 2 * k, IDESC, 1);
+                        for (int k = 0; k < 4; ++k) {
+                            mma_tf32_ts(d, a_lo + 8 * k, bh + 2 * k, IDESC, !(first && k == 0));
+                            mma_tf32_ts(d, a_hi + 8 * k, bl + 2 * k, IDESC, 1);
+                            mma_tf32_ts(d, a_hi + 8 * k, bh + 2 * k, IDESC, 1);
+                        }
+                        mma_commit(&afree[sa]);
+                        mma_commit(&xfree[sx]);
+                        if (last) mma_commit(&dfull[b]);
                     }
-                    mma_commit(&afree[sa]);
-                    mma_commit(&xfree[sx]);
-                    if ((i % CH_G) == CH_G - 1 || i == nch - 1) { mma_commit(&dfull[b]); ++gg; }
+                    __syncwarp();
+                    if (last) ++gg;
                 }
             }
+            mp.flush();
         }
-        __syncwarp();
     } else {
         // ================================ X warps: activations, promotion, partials, barriers, reduction ================================
         const int xt = tid - 128;                                   // 0..255
@@ -223,30 +289,92 @@ __global__ void __launch_bounds__(CH_THREADS, 1) ar_chain_kernel(const __grid_co
         const uint32_t lane_off = (uint32_t)(32 * (warp & 3)) << 16;
         constexpr int HB = CH_BN / 2;
         const int M = a.M;
+        ChainProbe probe;
+        probe.start(cta == 0 && xt == 0);
+        float4 *xraw = reinterpret_cast<float4 *>(smem + CH_OFF_XRAW);
+        float *s_ln = reinterpret_cast<float *>(smem + CH_OFF_LN);
+        // LayerNorm gamma / beta slices of this CTA's K ranges are weights: staged before the dependency wait
+        {
+            int lnp = 0;
+            for (int p = 0; p < a.n_phases; ++p) {
+                const ChainPhase &ph = a.ph[p];
+                if (!ph.ln_g) continue;
+                int tile, c_beg, c_end;
+                if (lnp < CH_LNP && unit_of(p, tile, c_beg, c_end) && c_end - c_beg <= CH_XR) {
+                    const int n = (c_end - c_beg) * 32;
+                    float *dst = s_ln + lnp * 2 * CH_XR * 32;
+                    for (int i = xt; i < 2 * n; i += CH_XT)
+                        dst[(i < n ? 0 : CH_XR * 32) + (i < n ? i : i - n)] = __ldg((i < n ? ph.ln_g : ph.ln_b) + c_beg * 32 + (i < n ? i : i - n));
+                }
+                ++lnp;
+            }
+        }
         pdl_wait();                                                 // everything below touches data of earlier kernels
+        probe.stamp(62);
         uint32_t it = 0, gg = 0;
-        int bar_i = 0;
+        int bar_i = 0, lnp = 0;
         for (int p = 0; p < a.n_phases; ++p) {
             const ChainPhase &ph = a.ph[p];
             if (ph.wait_before) { chain_grid_barrier(a.bar + bar_i, n_cta, xt); ++bar_i; }
+            probe.stamp(p * 8 + 0);
             int tile, c_beg, c_end;
             const bool has = unit_of(p, tile, c_beg, c_end);
+            const int my_lnp = ph.ln_g ? lnp++ : -1;
             if (has) {
                 const int K = ph.K;
-                // ---- LayerNorm row statistics: merge the (mean, M2) pieces of each row (Chan et al.)
+                const int nch = c_end - c_beg;
+                const int grp = xt >> 7, gt = xt & 127;     // the two X groups (warps 4-7 / 8-11) produce alternate chunks
+                // ---- prefetch of the activation chunks this thread will convert (chunks i with (i & 1) == grp): cp.async into
+                //      thread-private staging (the copying thread is the reading thread: no barrier), 4 own chunks in flight; one
+                //      commit group per slot, empty groups keep the group arithmetic uniform
+                auto issue_x = [&](int i) {
+                    const int k0 = (c_beg + i) * 32, slot = (i >> 1) % CH_XRL;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int idx = gt + 128 * j, r = idx >> 3, chk = idx & 7;
+                        cp_async16(xraw + (slot * 4 + j) * CH_XT + xt, ph.x + (size_t)(r < M ? r : 0) * K + k0 + chk * 4, r < M ? 16 : 0);
+                    }
+                };
+                // ---- LayerNorm row statistics (loads first, so that they do not queue behind the operand prefetch burst):
+                //      thread xt < M fetches the (mean, M2) pieces of row xt — 8 pieces = 64 bytes through cp.async into its private
+                //      slot when K <= 1024, plain loads otherwise — and merges them with Chan's formula
+                const int pieces = ph.ln_g ? (K + CH_STAT_COLS - 1) / CH_STAT_COLS : 0;
+                const bool st_async = pieces > 0 && pieces <= 8 && (pieces & 1) == 0;   // 16-byte aligned rows
+                float2 *my_st = reinterpret_cast<float2 *>(smem + CH_OFF_STST) + (xt & 63) * 8;
+                if (st_async && xt < M) {
+                    const float2 *sp = reinterpret_cast<const float2 *>(ph.stats_in) + (size_t)xt * pieces;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (2 * q < pieces) cp_async16(my_st + 2 * q, sp + 2 * q, 2 * q + 1 < pieces ? 16 : 8);
+                }
+                cp_async_commit();                           // group "statistics" (possibly empty)
+#pragma unroll
+                for (int li = 0; li < CH_XRL; ++li) {
+                    if (2 * li + grp < nch) issue_x(2 * li + grp);
+                    cp_async_commit();
+                }
                 if (ph.ln_g) {
                     if (xt < CH_BN) {
                         float mean = 0.f, rstd = 0.f;
                         if (xt < M) {
                             float n = 0.f, m2 = 0.f;
-                            const int pieces = (K + CH_ITEM_COLS - 1) / CH_ITEM_COLS;
-                            for (int q = 0; q < pieces; ++q) {
-                                const float2 st = __ldcg(reinterpret_cast<const float2 *>(ph.stats_in) + (size_t)xt * pieces + q);
-                                const float nb = (float)min(CH_ITEM_COLS, K - q * CH_ITEM_COLS);
-                                const float delta = st.x - mean, tot = n + nb;
-                                mean += delta * (nb / tot);
-                                m2 += st.y + delta * delta * (n * nb / tot);
-                                n = tot;
+                            const float2 *sp = reinterpret_cast<const float2 *>(ph.stats_in) + (size_t)xt * pieces;
+                            if (st_async) cp_async_wait<CH_XRL>();      // the statistics group has landed
+                            for (int q0 = 0; q0 < pieces; q0 += 8) {
+                                float2 stp[8];
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)      // 8 pieces in flight at once
+                                    if (q0 + q < pieces) stp[q] = st_async ? my_st[q] : __ldcg(sp + q0 + q);
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    if (q0 + q < pieces) {
+                                        const float nb = (float)min(CH_STAT_COLS, K - (q0 + q) * CH_STAT_COLS);
+                                        const float delta = stp[q].x - mean, tot = n + nb;
+                                        mean += delta * (nb / tot);
+                                        m2 += stp[q].y + delta * delta * (n * nb / tot);
+                                        n = tot;
+                                    }
+                                }
                             }
                             rstd = 1.0f / sqrtf(m2 / (float)K + 1e-5f);
                         }
@@ -254,12 +382,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) ar_chain_kernel(const __grid_co
                     }
                     bar_sync(3, CH_XT);
                 }
-                float acc[HB];             // acc[j] = D[row][half * 32 + j]
+                probe.stamp(p * 8 + 1);
+                constexpr int HBc = CH_BN / 2;
+                float acc[HBc];            // acc[j] = D[row][half * 32 + j]
 #pragma unroll
-                for (int j = 0; j < HB; ++j) acc[j] = 0.f;
+                for (int j = 0; j < HBc; ++j) acc[j] = 0.f;
                 auto drain = [&]() {          // acc += D[gg & 1]; advances gg
                     const uint32_t b = gg & 1;
                     mbar_wait(&dfull[b], (gg >> 1) & 1);
+                    probe.stamp(51);
                     tc_fence_after();
                     {
                         uint32_t v[32];
@@ -269,103 +400,124 @@ __global__ void __launch_bounds__(CH_THREADS, 1) ar_chain_kernel(const __grid_co
                         for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(v[j]);
                     }
                     tc_fence_before();
-                    mbar_arrive(&dfree[b]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&dfree[b]);
                     ++gg;
                 };
-                // thread -> 2 float4 of the 64 x 32 chunk: element idx = xt + 256 j: row = idx >> 3, 16-byte chunk = idx & 7
-                auto load_x = [&](int c, float4 (&v)[2]) {
-                    const int k0 = c * 32;
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int idx = xt + CH_XT * j, r = idx >> 3, chk = idx & 7;
-                        v[j] = r < M ? ldcg4(ph.x + (size_t)r * K + k0 + chk * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                };
-                const int nch = c_end - c_beg;
-                float4 cur[2], nxt[2];
-                load_x(c_beg, cur);
+                const bool ln_staged = my_lnp >= 0 && my_lnp < CH_LNP && nch <= CH_XR;
+                const float *sg = s_ln + (my_lnp < 0 ? 0 : my_lnp) * 2 * CH_XR * 32, *sb = sg + CH_XR * 32;
+                probe.stamp(p * 8 + 2);
                 int pending = 0;              // promotion groups committed by the MMA warp but not drained yet
                 for (int i = 0; i < nch; ++i, ++it) {
-                    if (i + 1 < nch) load_x(c_beg + i + 1, nxt);
-                    const uint32_t sx = it % CH_XS;
-                    if (it >= CH_XS) mbar_wait(&xfree[sx], ((it / CH_XS) - 1) & 1);
-                    float *xh = reinterpret_cast<float *>(smem + CH_OFF_XH + sx * CH_X_TILE);
-                    float *xl = reinterpret_cast<float *>(smem + CH_OFF_XL + sx * CH_X_TILE);
-                    const int k0 = (c_beg + i) * 32;
+                    if ((i & 1) == grp) {
+                        // ---- this group's chunk: staged fp32 -> (LayerNorm) -> TF32 hi / lo UMMA tiles
+                        probe.stamp(48);
+                        cp_async_wait<CH_XRL - 1>();       // this thread's copies of chunk i have landed
+                        const int slot = (i >> 1) % CH_XRL;
+                        float4 cur[4];
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int idx = xt + CH_XT * j, r = idx >> 3, chk = idx & 7;
-                        float4 v = cur[j];
-                        if (ph.ln_g && r < M) {
-                            const float mean = s_mean[r], rstd = s_rstd[r];
-                            const float4 g = __ldg(reinterpret_cast<const float4 *>(ph.ln_g + k0 + chk * 4));
-                            const float4 bb = __ldg(reinterpret_cast<const float4 *>(ph.ln_b + k0 + chk * 4));
-                            v.x = (v.x - mean) * rstd * g.x + bb.x;
-                            v.y = (v.y - mean) * rstd * g.y + bb.y;
-                            v.z = (v.z - mean) * rstd * g.z + bb.z;
-                            v.w = (v.w - mean) * rstd * g.w + bb.w;
+                        for (int j = 0; j < 4; ++j) cur[j] = xraw[(slot * 4 + j) * CH_XT + xt];
+                        if (i + 2 * CH_XRL < nch) issue_x(i + 2 * CH_XRL);
+                        cp_async_commit();
+                        const uint32_t sx = it % CH_XS;
+                        if (it >= CH_XS) mbar_wait(&xfree[sx], ((it / CH_XS) - 1) & 1);
+                        probe.stamp(49);
+                        float *xh = reinterpret_cast<float *>(smem + CH_OFF_XH + sx * CH_X_TILE);
+                        float *xl = reinterpret_cast<float *>(smem + CH_OFF_XL + sx * CH_X_TILE);
+                        const int k0 = (c_beg + i) * 32;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int idx = gt + 128 * j, r = idx >> 3, chk = idx & 7;
+                            float4 v = cur[j];
+                            if (ph.ln_g && r < M) {
+                                const float mean = s_mean[r], rstd = s_rstd[r];
+                                const float4 g = ln_staged ? ld4(sg + i * 32 + chk * 4) : __ldg(reinterpret_cast<const float4 *>(ph.ln_g + k0 + chk * 4));
+                                const float4 bb = ln_staged ? ld4(sb + i * 32 + chk * 4) : __ldg(reinterpret_cast<const float4 *>(ph.ln_b + k0 + chk * 4));
+                                v.x = (v.x - mean) * rstd * g.x + bb.x;
+                                v.y = (v.y - mean) * rstd * g.y + bb.y;
+                                v.z = (v.z - mean) * rstd * g.z + bb.z;
+                                v.w = (v.w - mean) * rstd * g.w + bb.w;
+                            }
+                            const int o = r * 32 + ((chk ^ (r & 7)) << 2);
+                            uint32_t h[4], l[4];
+                            split_tf32(v.x, h[0], l[0]); split_tf32(v.y, h[1], l[1]);
+                            split_tf32(v.z, h[2], l[2]); split_tf32(v.w, h[3], l[3]);
+                            *reinterpret_cast<uint4 *>(xh + o) = make_uint4(h[0], h[1], h[2], h[3]);
+                            *reinterpret_cast<uint4 *>(xl + o) = make_uint4(l[0], l[1], l[2], l[3]);
                         }
-                        const int o = r * 32 + ((chk ^ (r & 7)) << 2);
-                        uint32_t h[4], l[4];
-                        split_tf32(v.x, h[0], l[0]); split_tf32(v.y, h[1], l[1]);
-                        split_tf32(v.z, h[2], l[2]); split_tf32(v.w, h[3], l[3]);
-                        *reinterpret_cast<uint4 *>(xh + o) = make_uint4(h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<uint4 *>(xl + o) = make_uint4(l[0], l[1], l[2], l[3]);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&xfull[sx]);
+                        probe.stamp(50);
                     }
-                    fence_proxy_async_smem();
-                    mbar_arrive(&xfull[sx]);
                     if ((i % CH_G) == CH_G - 1 || i == nch - 1) {
-                        // group g of this unit handed over: promote the previous one (its MMAs finished long ago)
+                        // promotion group g of this unit is in the MMA warp's hands: promote the previous one
                         if (pending > 0) { drain(); --pending; }
                         ++pending;
                     }
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) cur[j] = nxt[j];
                 }
+                cp_async_wait<0>();
                 while (pending > 0) { drain(); --pending; }
+                probe.stamp(p * 8 + 3);
                 // ---- partial tile of this (tile, split) unit -> L2 scratch [unit][m][128]
                 float *part = a.scratch + ((size_t)cta * CH_BN + half * HB) * 128 + row;
 #pragma unroll
                 for (int j = 0; j < HB; ++j)
                     if (half * HB + j < M) __stcg(part + j * 128, acc[j]);
+                probe.stamp(p * 8 + 4);
             }
             if (ph.tiles > 0) { chain_grid_barrier(a.bar + bar_i, n_cta, xt); ++bar_i; }
-            // ---- distributed reduction: items (row m, 512-column block cb), by the first 128 X threads
-            if (xt < 128) {
+            probe.stamp(p * 8 + 5);
+            // ---- distributed reduction: items (row m, 512-column block cb); the two groups of 128 X threads take alternate
+            //      items; every load of an item is issued before the first use; LayerNorm statistics per warp (128 columns)
+            {
+                const int grp = xt >> 7, gt = xt & 127, wq = gt >> 5;
                 const int N = ph.N, S = ph.tiles > 0 ? ph.splits : 0;
-                const int CB = (N + CH_ITEM_COLS - 1) / CH_ITEM_COLS;
+                const int CB = (N + CH_ITEM_COLS - 1) / CH_ITEM_COLS, PC = (N + CH_STAT_COLS - 1) / CH_STAT_COLS;
                 const bool vec = (N & 3) == 0;
-                for (int item = cta; item < M * CB; item += n_cta) {
+                for (int item = cta + grp * n_cta; item < M * CB; item += 2 * n_cta) {
                     const int m = item / CB, cb = item % CB;
-                    const int n = cb * CH_ITEM_COLS + xt * 4;
-                    const int cnt = min(CH_ITEM_COLS, N - cb * CH_ITEM_COLS);
-                    float v[4] = {0.f, 0.f, 0.f, 0.f};
+                    const int n = cb * CH_ITEM_COLS + gt * 4;
                     const int nv = max(0, min(4, N - n));      // valid columns of this thread
+                    float v[4] = {0.f, 0.f, 0.f, 0.f};
                     if (nv > 0) {
-                        if (S > 0) {
-                            const int t = n >> 7, nl = n & 127;
-                            const float *src = a.scratch + (((size_t)t * S) * CH_BN + m) * 128 + nl;
-                            // two batches of <= 9 independent loads in flight; summed in split order (deterministic)
+                        const int t = n >> 7, nl = n & 127;
+                        const float *src = a.scratch + (((size_t)t * S) * CH_BN + m) * 128 + nl;
+                        float4 pv[9];
+                        float bs[4] = {0.f, 0.f, 0.f, 0.f}, rs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                            for (int s0 = 0; s0 < 18; s0 += 9) {
-                                float4 pv[9];
+                        for (int s = 0; s < 9; ++s)
+                            if (s < S) pv[s] = ldcg4(src + (size_t)s * CH_BN * 128);
+                        if (vec) {
+                            if (ph.bias) { const float4 b4 = __ldg(reinterpret_cast<const float4 *>(ph.bias + n)); bs[0] = b4.x; bs[1] = b4.y; bs[2] = b4.z; bs[3] = b4.w; }
+                            if (ph.residual) { const float4 r4 = ldcg4(ph.residual + (size_t)m * N + n); rs[0] = r4.x; rs[1] = r4.y; rs[2] = r4.z; rs[3] = r4.w; }
+                        } else {
 #pragma unroll
-                                for (int s = 0; s < 9; ++s)
-                                    if (s0 + s < S) pv[s] = ldcg4(src + (size_t)(s0 + s) * CH_BN * 128);
-#pragma unroll
-                                for (int s = 0; s < 9; ++s)
-                                    if (s0 + s < S) { v[0] += pv[s].x; v[1] += pv[s].y; v[2] += pv[s].z; v[3] += pv[s].w; }
+                            for (int q = 0; q < 4; ++q) {
+                                if (q < nv) {
+                                    if (ph.bias) bs[q] = __ldg(ph.bias + n + q);
+                                    if (ph.residual) rs[q] = __ldcg(ph.residual + (size_t)m * N + n + q);
+                                }
                             }
                         }
 #pragma unroll
+                        for (int s = 0; s < 9; ++s)
+                            if (s < S) { v[0] += pv[s].x; v[1] += pv[s].y; v[2] += pv[s].z; v[3] += pv[s].w; }
+                        if (S > 9) {                             // splits 9..17, still in split order (deterministic)
+#pragma unroll
+                            for (int s = 0; s < 9; ++s)
+                                if (9 + s < S) pv[s] = ldcg4(src + (size_t)(9 + s) * CH_BN * 128);
+#pragma unroll
+                            for (int s = 0; s < 9; ++s)
+                                if (9 + s < S) { v[0] += pv[s].x; v[1] += pv[s].y; v[2] += pv[s].z; v[3] += pv[s].w; }
+                        }
+#pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            if (q < nv) {
-                                float t = v[q];
-                                if (ph.bias) t += __ldg(ph.bias + n + q);
-                                if (ph.act == 1) t = gelu_erf_ch(t);
-                                if (ph.residual) t += __ldcg(ph.residual + (size_t)m * N + n + q);
-                                v[q] = t;
-                            }
+                            float tq = v[q];
+                            if (ph.bias) tq += bs[q];
+                            if (ph.act == 1) tq = gelu_erf_ch(tq);
+                            if (ph.residual) tq += rs[q];
+                            v[q] = q < nv ? tq : 0.f;
                         }
                         if (ph.y) {
                             float *dst = ph.y + (size_t)m * N + n;
@@ -375,17 +527,22 @@ __global__ void __launch_bounds__(CH_THREADS, 1) ar_chain_kernel(const __grid_co
                         }
                     }
                     if (ph.stats_out) {
-                        float s = 0.f;
-                        for (int q = 0; q < nv; ++q) s += v[q];
-                        const float mean = x_block_sum(s, s_red, xt) / (float)cnt;
+                        // (mean, M2) of this warp's 128 columns of row m — merged by the consumer (Chan et al.)
+                        const int piece = cb * (CH_ITEM_COLS / CH_STAT_COLS) + wq;
+                        const int cnt = max(0, min(CH_STAT_COLS, N - piece * CH_STAT_COLS));
+                        const float mean = warp_sum((v[0] + v[1]) + (v[2] + v[3])) / (float)max(cnt, 1);
                         float d2 = 0.f;
-                        for (int q = 0; q < nv; ++q) d2 += (v[q] - mean) * (v[q] - mean);
-                        const float m2 = x_block_sum(d2, s_red, xt);
-                        if (xt == 0) __stcg(reinterpret_cast<float2 *>(ph.stats_out) + (size_t)m * CB + cb, make_float2(mean, m2));
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (q < nv) d2 += (v[q] - mean) * (v[q] - mean);
+                        const float m2 = warp_sum(d2);
+                        if (lane == 0 && cnt > 0) __stcg(reinterpret_cast<float2 *>(ph.stats_out) + (size_t)m * PC + piece, make_float2(mean, m2));
                     }
                 }
             }
+            probe.stamp(p * 8 + 6);
         }
+        probe.flush();
         // ---- reset the barrier counters for the next launch: the last CTA to get here knows everybody passed every barrier
         bar_sync(2, CH_XT);
         if (xt == 0) {
@@ -440,6 +597,11 @@ int chain_weight_map(const float *W, int N, int K, void *map_out) {
                            gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled"); return SFB200_E_CUDA; }
+    return SFB200_OK;
+}
+
+int set_chain_timeline(unsigned long long *buf) {
+    SFB_CUDA_TRY(cudaMemcpyToSymbol(g_chain_timeline, &buf, sizeof(buf)));
     return SFB200_OK;
 }
 

@@ -115,7 +115,7 @@ static void carve(const sfb200_ar_config *c, Buffers *b) {
     b->logp = take(B * (int64_t)c->max_steps * 2 * F);
     b->att_cnt = take(B * c->n_head * 4);
     b->ch_bar = take((CH_MAX_BARRIERS + 1) * 4);
-    b->ch_stats = take(64 * ((d + 511) / 512) * 2 * F);
+    b->ch_stats = take(64 * ((d + 127) / 128) * 2 * F);
     b->ch_scratch = take((int64_t)chain_scratch_floats(CHAIN_MAX_GRID) * F);
     b->total = o;
 }

@@ -51,11 +51,11 @@ struct alignas(64) TensorMapBlob { unsigned char b[128]; };   // a CUtensorMap (
 struct ChainPhase {
     const float *x;          // (M, K) input activations (GEMM phases)
     const float *ln_g, *ln_b;   // LayerNorm weight / bias applied to x on load, or NULL
-    const float *stats_in;   // (M, ceil(K/512), 2) per-row (mean, M2) pieces of x when ln_g != NULL
+    const float *stats_in;   // (M, ceil(K/128), 2) per-row (mean, M2) pieces of x when ln_g != NULL
     const float *bias;       // (N) or NULL
     const float *residual;   // (M, N) or NULL (may alias y)
     float *y;                // (M, N) output, or NULL (statistics-only phase)
-    float *stats_out;        // (M, ceil(N/512), 2) pieces of the OUTPUT rows (a LayerNorm follows), or NULL
+    float *stats_out;        // (M, ceil(N/128), 2) pieces of the OUTPUT rows (a LayerNorm follows), or NULL
     int N, K;
     int tiles, splits;       // tiles = ceil(N/128); tiles * splits <= grid.  tiles == 0: no GEMM, the reduction step only sees
                              // `residual` (used to produce stats_out for a row vector written by an earlier kernel)
@@ -74,6 +74,7 @@ int chain_grid_size();
 void chain_plan(int N, int K, int grid, int *tiles, int *splits);
 size_t chain_scratch_floats(int grid);
 int launch_chain(const ChainArgs &args, cudaStream_t stream);
+int set_chain_timeline(unsigned long long *buf);
 
 int launch_attn_decode(const float *qkv, float *kc, float *vc, float *out, float *part, int B, int H, int max_len, int pos,
                        const int32_t *st, int n_split, cudaStream_t s, int group = 1, int lcond = 0, int lcond_delta = 0);

@@ -21,7 +21,7 @@ namespace sfb {
 using namespace tc;
 
 constexpr int AG_TK = 16;                 // keys per tile
-constexpr int AG_NS = 3;                  // ring stages
+constexpr int AG_NS = 5;                  // ring stages (40 KB per CTA: 5 CTAs per SM keep ~160 KB of K/V in flight)
 constexpr int AG_TILE = AG_TK * 64 * 4;   // 4 KB (K or V)
 constexpr int AG_MRG = 68;                // merge row stride (floats)
 constexpr int AG_PARTS = 3;               // partial states per (row, head)

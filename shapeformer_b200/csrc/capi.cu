@@ -89,8 +89,8 @@ int sfb200_linear_tc_ps(const float *x, const float *Wt, const float *bias, cons
     if (!x || !Wt || !y || (act != 0 && act != 1)) return SFB200_E_ARG;
     return launch_linear_tc_ps(x, Wt, bias, residual, y, M, N, K, act, as_stream(stream));
 }
-// workspace of sfb200_chain_linear: [barrier counters 256 B | row statistics 64 x 8 pieces x 2 floats | split-K partials]
-static const int64_t kChainWsBar = 256, kChainWsStats = 64 * 8 * 2 * 4;
+// workspace of sfb200_chain_linear: [barrier counters 256 B | row statistics 64 x 32 pieces x 2 floats | split-K partials]
+static const int64_t kChainWsBar = 256, kChainWsStats = 64 * 32 * 2 * 4;
 int64_t sfb200_chain_workspace_bytes(void) { return kChainWsBar + kChainWsStats + (int64_t)chain_scratch_floats(160) * 4; }
 int sfb200_chain_linear(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
                         int act, const float *ln_w, const float *ln_b, void *workspace, void *stream) {
@@ -119,6 +119,7 @@ int sfb200_chain_linear(const float *x, const float *W, const float *bias, const
     chain_plan(N, K, grid, &ph.tiles, &ph.splits);
     return launch_chain(a, as_stream(stream));
 }
+int sfb200_debug_chain_timeline(void *buf128) { return set_chain_timeline(static_cast<unsigned long long *>(buf128)); }
 int sfb200_debug_ps_timeline(void *buf16) { return set_ps_timeline(static_cast<unsigned long long *>(buf16)); }
 int sfb200_layernorm(const float *x, const float *w, const float *b, float *y, int rows, int d, void *stream) {
     if (!x || !w || !b || !y) return SFB200_E_ARG;

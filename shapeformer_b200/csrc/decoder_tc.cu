@@ -199,8 +199,9 @@ decoder_points_tc_kernel(const float *__restrict__ grid, const float *__restrict
             if (valid) out[(size_t)b * N + n] = o;
         }
         tc_fence_before();
-    } else if (lane == 0) {
+    } else {
         // =========================================== MMA issuer ===========================================
+        // the whole warp stays converged and one elected lane issues: descriptors live in uniform registers (tc_common.cuh)
         constexpr uint32_t IDESC160 = instr_desc(2, 128, 160), IDESC32 = instr_desc(2, 128, 32);
         const uint32_t wc_hi = smem_u32(dsm + DTC_OFF_WC_HI), wc_lo = smem_u32(dsm + DTC_OFF_WC_LO);
         const uint32_t w0 = smem_u32(dsm + DTC_OFF_W);
@@ -218,25 +219,31 @@ decoder_points_tc_kernel(const float *__restrict__ grid, const float *__restrict
                     const uint32_t a_hi = tgb + DTC_COL_A, a_lo = a_hi + 32;
                     if (step == 0) {
                         const uint64_t bh = smem_desc_k128(wc_hi), bl = smem_desc_k128(wc_lo);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            mma_tf32_ts(tgb, a_lo + 8 * k, bh + 2 * k, IDESC160, k != 0);
-                            mma_tf32_ts(tgb, a_hi + 8 * k, bl + 2 * k, IDESC160, 1);
-                            mma_tf32_ts(tgb, a_hi + 8 * k, bh + 2 * k, IDESC160, 1);
+                            for (int k = 0; k < 4; ++k) {
+                                mma_tf32_ts(tgb, a_lo + 8 * k, bh + 2 * k, IDESC160, k != 0);
+                                mma_tf32_ts(tgb, a_hi + 8 * k, bl + 2 * k, IDESC160, 1);
+                                mma_tf32_ts(tgb, a_hi + 8 * k, bh + 2 * k, IDESC160, 1);
+                            }
+                            mma_commit(&done[g]);
                         }
                     } else {
                         const int mtx = step - 1;   // (blk, fc_0 / fc_1)
                         const uint64_t bh = smem_desc_k128(w0 + (mtx * 2) * DTC_TILE_W);
                         const uint64_t bl = smem_desc_k128(w0 + (mtx * 2 + 1) * DTC_TILE_W);
                         const uint32_t d = tgb + DTC_COL_D;
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            mma_tf32_ts(d, a_lo + 8 * k, bh + 2 * k, IDESC32, k != 0);
-                            mma_tf32_ts(d, a_hi + 8 * k, bl + 2 * k, IDESC32, 1);
-                            mma_tf32_ts(d, a_hi + 8 * k, bh + 2 * k, IDESC32, 1);
+                            for (int k = 0; k < 4; ++k) {
+                                mma_tf32_ts(d, a_lo + 8 * k, bh + 2 * k, IDESC32, k != 0);
+                                mma_tf32_ts(d, a_hi + 8 * k, bl + 2 * k, IDESC32, 1);
+                                mma_tf32_ts(d, a_hi + 8 * k, bh + 2 * k, IDESC32, 1);
+                            }
+                            mma_commit(&done[g]);
                         }
                     }
-                    mma_commit(&done[g]);
+                    __syncwarp();
                 }
             }
         }

@@ -134,6 +134,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
+// One lane of a fully converged warp.  Keep the MMA-issuing warp CONVERGED and predicate only the tcgen05 instructions with
+// this: operands computed by warp-uniform code stay in uniform registers, whereas a loop running under `if (lane == 0)` makes
+// the compiler re-broadcast every descriptor with ELECT + R2UR sequences before each UTCHMMA (~50 cycles per MMA).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // named barrier among a subset of warps
 __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory"); }
 

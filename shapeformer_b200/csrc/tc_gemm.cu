@@ -199,7 +199,7 @@ tc_linear_kernel(const float *x, const float *__restrict__ W, const float *__res
     } else {
         // ================================ MMA issuer (one elected thread of warp 4) ================================
         pdl_wait();
-        if ((tid & 31) == 0) {   // warp 8
+        {   // warp 8: the whole warp stays converged, one elected lane issues (operands stay in uniform registers)
             const uint32_t xh0 = smem_u32(smem + L::OFF_XH), xl0 = smem_u32(smem + L::OFF_XL);
             for (int i = 0; i < nch; ++i) {
                 const int slot = i % TCG_NT, g = i / TCG_G, b = g & 1;
@@ -212,18 +212,20 @@ tc_linear_kernel(const float *x, const float *__restrict__ W, const float *__res
                 const uint32_t d = tmem_base + b * BN;
                 const uint32_t a_hi = tmem_base + A_COL0 + slot * 64, a_lo = a_hi + 32;
                 const uint64_t bh = smem_desc_k128(xh0 + slot * L::X_TILE), bl = smem_desc_k128(xl0 + slot * L::X_TILE);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    // small products first, the dominant hi*hi term last
-                    mma_tf32_ts(d, a_lo + 8 * k, bh + 2 * k, IDESC, !(first && k == 0));
-                    mma_tf32_ts(d, a_hi + 8 * k, bl + 2 * k, IDESC, 1);
-                    mma_tf32_ts(d, a_hi + 8 * k, bh + 2 * k, IDESC, 1);
+                    for (int k = 0; k < 4; ++k) {
+                        // small products first, the dominant hi*hi term last
+                        mma_tf32_ts(d, a_lo + 8 * k, bh + 2 * k, IDESC, !(first && k == 0));
+                        mma_tf32_ts(d, a_hi + 8 * k, bl + 2 * k, IDESC, 1);
+                        mma_tf32_ts(d, a_hi + 8 * k, bh + 2 * k, IDESC, 1);
+                    }
+                    mma_commit(&done[slot]);
+                    if ((i % TCG_G) == TCG_G - 1 || i == nch - 1) mma_commit(&dfull[b]);
                 }
-                mma_commit(&done[slot]);
-                if ((i % TCG_G) == TCG_G - 1 || i == nch - 1) mma_commit(&dfull[b]);
+                __syncwarp();
             }
         }
-        __syncwarp();
     }
     tc_fence_before();
     __syncthreads();      // operand ring is idle from here on; TMEM is no longer needed

@@ -173,7 +173,7 @@ tc_linear_ps_kernel(const float *x, const float *__restrict__ Wt, const float *_
     } else if (warp == 4) {
         // ================================ MMA issuer ================================
         pdl_wait();
-        if ((tid & 31) == 0) {
+        {   // the whole warp stays converged, one elected lane issues (operands stay in uniform registers)
             const uint32_t w0 = smem_u32(smem + PS_OFF_W), xh0 = smem_u32(smem + PS_OFF_XH), xl0 = smem_u32(smem + PS_OFF_XL);
             for (int i = 0; i < nch; ++i) {
                 const int s = i % PS_NS, g = i / PS_G, b = g & 1;
@@ -182,22 +182,24 @@ tc_linear_ps_kernel(const float *x, const float *__restrict__ Wt, const float *_
                 mbar_wait(&wfull[s], (i / PS_NS) & 1);
                 mbar_wait(&xfull[s], (i / PS_NS) & 1);
                 tc_fence_after();
-                if (i == 0) ps_stamp(4);
+                if (i == 0 && (tid & 31) == 0) ps_stamp(4);
                 const uint32_t d = tmem_base + b * PS_BN;
                 const uint64_t ah = smem_desc_k128(w0 + s * PS_W_STAGE), al = smem_desc_k128(w0 + s * PS_W_STAGE + 16384);
                 const uint64_t bh = smem_desc_k128(xh0 + s * PS_X_TILE), bl = smem_desc_k128(xl0 + s * PS_X_TILE);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    mma_tf32_ss(d, al + 2 * k, bh + 2 * k, IDESC, !(first && k == 0));
-                    mma_tf32_ss(d, ah + 2 * k, bl + 2 * k, IDESC, 1);
-                    mma_tf32_ss(d, ah + 2 * k, bh + 2 * k, IDESC, 1);
+                    for (int k = 0; k < 4; ++k) {
+                        mma_tf32_ss(d, al + 2 * k, bh + 2 * k, IDESC, !(first && k == 0));
+                        mma_tf32_ss(d, ah + 2 * k, bl + 2 * k, IDESC, 1);
+                        mma_tf32_ss(d, ah + 2 * k, bh + 2 * k, IDESC, 1);
+                    }
+                    mma_commit(&done[s]);
+                    if ((i % PS_G) == PS_G - 1 || i == nch - 1) mma_commit(&dfull[b]);
                 }
-                mma_commit(&done[s]);
-                if ((i % PS_G) == PS_G - 1 || i == nch - 1) mma_commit(&dfull[b]);
+                __syncwarp();
             }
-            ps_stamp(5);
+            if ((tid & 31) == 0) ps_stamp(5);
         }
-        __syncwarp();
     } else {
         // ================================ weight loader (TMA bulk copies) ================================
         // weights are constants: no dependency wait before streaming them
