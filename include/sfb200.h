@@ -78,6 +78,43 @@ int sfb200_tokens_to_dense(const int64_t *tokens, const int64_t *empty_index, in
                            int64_t end_pos, int64_t end_val, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * VQDIF encoder + quantiser: partial point cloud -> code grid -> (pos, val) conditioning tuples   
+ *   LocalPoolPointnet.forward vqdif/enc.py:66-140, Downsampler vqdif/updown.py:98-113, Quantizer.forward vqdif/quantizer.py:31-53,
+ *   VQDIF.quantize_cloud vqdif/vqdif.py:50-58, batch_dense2sparse shapeformer/common.py:84-122,152-169
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* Device pointers to the encoder weights (shipped shapenet_res16 shapes: hidden = c_dim = 32, 5 ResNet-FC blocks, 64^3 scatter
+ * grid, Downsampler 32 -> 64 -> 128 over two k2s2 + k1 'crg' pairs, 128-d codes).  Linear weights are (out, in) row-major like
+ * the state_dict; ds_wT[i] = encoder.downsampler.blocks.i.conv.weight.permute(2, 3, 4, 1, 0) made contiguous = (k^3 * Cin, Cout). */
+typedef struct sfb200_enc_weights {
+    const float *fc_pos_w, *fc_pos_b;                  /* (64, 3), (64) */
+    const float *fc0_w[5], *fc0_b[5];                  /* blocks.i.fc_0: (32, 64), (32) */
+    const float *fc1_w[5], *fc1_b[5];                  /* blocks.i.fc_1: (32, 32), (32) */
+    const float *sc_w[5];                              /* blocks.i.shortcut.weight: (32, 64) */
+    const float *fcc_w, *fcc_b;                        /* fc_c: (32, 32), (32) */
+    const float *ds_wT[4], *ds_gn_w[4], *ds_gn_b[4];   /* Downsampler convs (transposed, see above) + GroupNorm(8) affine */
+    const float *codebook;                             /* quantizer.embedding.weight (n_codes, 128) */
+    int n_codes;
+} sfb200_enc_weights;
+
+/* Bytes of device workspace for sfb200_encode_cloud with B clouds of T points (about 150 MB per cloud). */
+int64_t sfb200_encoder_workspace_bytes(int B, int T, int n_codes);
+
+/* VQDIF.encode + Quantizer.forward: cloud (B, T, 3) fp32 in [-1, 1] -> raw_ind (B, 16, 16, 16) int64 nearest-code indices of
+ * every cell, mask (B, 16^3) uint8 = cells that contain a point (enc.py:84-91, layout [z][y][x]), and optionally grid_feat
+ * (B, 128, 16^3) fp32, the encoder output the reference feeds to the quantiser. */
+int sfb200_encode_cloud(const sfb200_enc_weights *w, const float *cloud, int B, int T, void *workspace, int64_t *raw_ind,
+                        unsigned char *mask, float *grid_feat, void *stream);
+
+/* VQDIF.quantize_cloud + batch_dense2sparse: modes[0] = most frequent raw index of the whole batch (smallest on ties), dense =
+ * mask ? raw : modes[0]; modes[1] = mode of dense (the empty index); tokens (B, max_len, 2) = per row the cells != modes[1] in
+ * raveled order as (pos, val), padded with the end tokens; lengths[b] = number of such cells (may exceed max_len: the caller
+ * crops like unpack_sparse).  workspace: n_codes int32. */
+int sfb200_dense_to_tokens(const int64_t *raw_ind, const unsigned char *mask, int B, int cells, int n_codes, int max_len,
+                           int64_t end_pos, int64_t end_val, void *workspace, int64_t *dense, int64_t *tokens, int32_t *lengths,
+                           int64_t *modes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Autoregressive sampler  (shapeformer/shapeformer.py:54-123, transformer/mingpt.py:46-111,185-319,
  *                          shapeformer/representers.py:120-155,187-196,432-442, shapeformer/common.py:260-299)
  * ------------------------------------------------------------------------------------------------------------------ */

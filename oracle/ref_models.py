@@ -55,6 +55,18 @@ def ref_vqdif_decoder(sd):
     return dec.eval(), q.eval()
 
 
+def ref_vqdif_encoder(sd):
+    """Reference LocalPoolPointnet (shipped shapenet_res16 kwargs) loaded from a synthetic VQDIF state dict; its torch_scatter
+    calls run through the scatter_reduce stand-in of oracle/ref_shim.py."""
+    ref_shim.reference_modules()
+    import importlib
+    enc_mod = importlib.import_module("shapeformer.models.vqdif.enc")
+    enc = enc_mod.LocalPoolPointnet(hidden_dim=32, plane_type="grid", grid_resolution=64, c_dim=32, downsampler=True,
+                                    downsampler_kwargs=dict(in_channels=32, downsample_steps=2))
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}, strict=True)
+    return enc.eval()
+
+
 def ref_decode_index(dec, q, code_ind, Xtg):
     """VQDIF.decode_index restated with the reference's own modules (vqdif/vqdif.py:60-76)."""
     with torch.no_grad():

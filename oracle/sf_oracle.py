@@ -442,3 +442,107 @@ def tokens_to_dense(tokens, empty_index, res=16, end_tokens=(4096, 4096)):
     for i in range(t.shape[0]):
         dense[int(t[i, 0])] = int(t[i, 1])
     return dense.view(res, res, res)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# VQDIF encoder + quantiser + token packing  (the step before the hot path)
+# ----------------------------------------------------------------------------------------------------------------------
+def _resnet_fc(sd, pre, x):
+    """ResnetBlockFC.forward — vqdif/layers.py:39-48 (shortcut when size_in != size_out)."""
+    net = F.linear(F.relu(x), sd[pre + "fc_0.weight"], sd[pre + "fc_0.bias"])
+    dx = F.linear(F.relu(net), sd[pre + "fc_1.weight"], sd[pre + "fc_1.bias"])
+    xs = F.linear(x, sd[pre + "shortcut.weight"]) if (pre + "shortcut.weight") in sd else x
+    return xs + dx
+
+
+def encoder_forward(sd, p, reso=64, pre="encoder."):
+    """LocalPoolPointnet.forward + generate_grid_features — vqdif/enc.py:66-140 (plane_type 'grid', scatter 'max',
+    c2i_order 'original', downsampler with 2 steps).  p (B,T,3) in [-0.5,0.5] -> (grid_feat (B,128,16,16,16), mask
+    (B,16,16,16) bool).  torch_scatter is restated with Tensor.scatter_reduce (max: empty cells 0, only gathered where
+    points exist; mean: include_self=False)."""
+    B, T, _ = p.shape
+    p_nor = normalize_3d(p.clone())
+    xi = (p_nor * reso).long()
+    index = xi[..., 0] + reso * (xi[..., 1] + reso * xi[..., 2])                 # (B,T)  coordinate2index, 'original'
+    net = F.linear(p, sd[pre + "fc_pos.weight"], sd[pre + "fc_pos.bias"])
+    net = _resnet_fc(sd, pre + "blocks.0.", net)
+    n_blocks = 1
+    while (pre + f"blocks.{n_blocks}.fc_0.weight") in sd:
+        n_blocks += 1
+    for i in range(1, n_blocks):
+        C = net.shape[2]
+        idx = index[:, :, None].expand(-1, -1, C)
+        pooled = torch.zeros(B, reso ** 3, C).scatter_reduce(1, idx, net, reduce="amax", include_self=False)
+        pooled = torch.gather(pooled, 1, idx)                                    # pool_local, enc.py:96-114
+        net = _resnet_fc(sd, pre + f"blocks.{i}.", torch.cat([net, pooled], 2))
+    c = F.linear(net, sd[pre + "fc_c.weight"], sd[pre + "fc_c.bias"])             # (B,T,c_dim)
+    C = c.shape[2]
+    idx = index[:, :, None].expand(-1, -1, C)
+    fea = torch.zeros(B, reso ** 3, C).scatter_reduce(1, idx, c, reduce="mean", include_self=False)
+    fea = fea.permute(0, 2, 1).reshape(B, C, reso, reso, reso)                    # enc.py:72-74
+    i = 0
+    while (pre + f"downsampler.blocks.{i}.conv.weight") in sd:                    # Downsampler 'crg', updown.py:98-113
+        dp = pre + f"downsampler.blocks.{i}."
+        k = sd[dp + "conv.weight"].shape[-1]
+        fea = F.relu(F.conv3d(fea, sd[dp + "conv.weight"], None, stride=k, padding=0))
+        fea = F.group_norm(fea, 8, sd[dp + "groupnorm.weight"], sd[dp + "groupnorm.bias"], 1e-5)
+        i += 1
+    R = fea.shape[-1]
+    mi = (p_nor * R).long()                                                       # enc.py:84-91
+    mask = torch.zeros(B, R, R, R, dtype=torch.bool)
+    b = torch.arange(B)[:, None].expand(-1, T)
+    mask[b, mi[..., 2], mi[..., 1], mi[..., 0]] = True
+    return fea, mask
+
+
+def quantize(sd, grid_feat, key="quantizer.embedding.weight"):
+    """Quantizer.forward (eval) — vqdif/quantizer.py:31-53: nearest code by |x|^2 - 2 x.w + |w|^2, first index on ties.
+    Returns (quant_ind (B,R,R,R) int64, distances (B*R^3, n_codes))."""
+    B, C = grid_feat.shape[:2]
+    flat = grid_feat.permute(0, 2, 3, 4, 1).contiguous().view(-1, C)
+    w = sd[key]
+    dist = (flat ** 2).sum(1, keepdim=True) - 2 * torch.mm(flat, w.t()) + (w.t() ** 2).sum(0, keepdim=True)
+    ind = torch.max(-dist, dim=1)[1]
+    return ind.view(B, *grid_feat.shape[2:]), dist
+
+
+def mode_smallest(x):
+    """pth_get_mode — shapeformer/common.py:20-23 (= torch.mode: the smallest of the most frequent values)."""
+    vals, counts = torch.unique(x.reshape(-1), return_counts=True)
+    return vals[torch.argmax(counts)]
+
+
+def quantize_cloud(sd, cloud):
+    """VQDIF.quantize_cloud — vqdif/vqdif.py:36-58: cloud (B,T,3) in [-1,1] -> (quant_ind with the batch-wide mode in
+    unoccupied cells, mode, raw quant_ind, mask)."""
+    fea, mask = encoder_forward(sd, cloud / 2.0)
+    raw, _ = quantize(sd, fea)
+    mode = mode_smallest(raw)
+    out = torch.zeros_like(raw) + mode
+    out[mask] = raw[mask]
+    return out, mode, raw, mask
+
+
+def batch_dense2sparse(indices, max_length=None, end_tokens=(4096, 4096)):
+    """batch_dense2sparse + unpack_sparse — shapeformer/common.py:84-122,152-169: (B,R,R,R) -> ((B,L,2) int64 padded with
+    end tokens, L = longest row + 1, cropped to max_length with a forced final end tuple; mode)."""
+    B = indices.shape[0]
+    flat = indices.reshape(B, -1)
+    mode = torch.mode(indices.reshape(-1))[0]
+    rows = [torch.stack([(flat[b] != mode).nonzero()[:, 0], flat[b][flat[b] != mode]], 1) for b in range(B)]
+    L = max(r.shape[0] for r in rows) + 1
+    out = torch.tensor(list(end_tokens), dtype=torch.int64).repeat(B, L, 1)
+    for b, r in enumerate(rows):
+        out[b, :r.shape[0]] = r
+    if max_length is not None and L > max_length:
+        out = out[:, :max_length].clone()
+        out[:, max_length - 1] = torch.tensor(list(end_tokens))
+    return out, mode
+
+
+def get_indices(sd, Xct, max_length=406, end_tokens=(4096, 4096)):
+    """AR_N.encode_cloud + get_indices for inference (Xbd None) — shapeformer/representers.py:68-103: partial cloud (B,T,3)
+    -> (c_indices (B,L_c,2), empty_index (mode))."""
+    quant_ind, _, _, _ = quantize_cloud(sd, Xct)
+    c_indices, mode = batch_dense2sparse(quant_ind, max_length, end_tokens)
+    return c_indices, mode

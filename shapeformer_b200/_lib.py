@@ -31,6 +31,17 @@ class ArSampling(ctypes.Structure):
     ]
 
 
+class EncWeights(ctypes.Structure):
+    """struct sfb200_enc_weights"""
+    _fields_ = [
+        ("fc_pos_w", c_f32p), ("fc_pos_b", c_f32p),
+        ("fc0_w", c_f32p * 5), ("fc0_b", c_f32p * 5), ("fc1_w", c_f32p * 5), ("fc1_b", c_f32p * 5), ("sc_w", c_f32p * 5),
+        ("fcc_w", c_f32p), ("fcc_b", c_f32p),
+        ("ds_wT", c_f32p * 4), ("ds_gn_w", c_f32p * 4), ("ds_gn_b", c_f32p * 4),
+        ("codebook", c_f32p), ("n_codes", ctypes.c_int),
+    ]
+
+
 # tensor ids of sfb200_ar_weight_offset
 (W_POS_EMB, W_COND_POS_EMB, W_TOK_EMB0, W_TOK_EMB1, W_EXTRA_EMB, W_HEAD_LN_W, W_HEAD_LN_B, W_HEAD_W, W_LN1_W, W_LN1_B,
  W_QKV_W, W_QKV_B, W_PROJ_W, W_PROJ_B, W_LN2_W, W_LN2_B, W_FC1_W, W_FC1_B, W_FC2_W, W_FC2_B, W_COUNT) = range(21)
@@ -50,6 +61,10 @@ SIGNATURES = {
                                              ctypes.c_int, ctypes.c_int, vp]),
     "sfb200_tokens_to_dense": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64,
                                               ctypes.c_int64, vp]),
+    "sfb200_encoder_workspace_bytes": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "sfb200_encode_cloud": (ctypes.c_int, [ctypes.POINTER(EncWeights), vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp]),
+    "sfb200_dense_to_tokens": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64,
+                                              ctypes.c_int64, vp, vp, vp, vp, vp, vp]),
     "sfb200_ar_weight_floats": (ctypes.c_int64, [ctypes.POINTER(ArConfig)]),
     "sfb200_ar_weight_offset": (ctypes.c_int64, [ctypes.POINTER(ArConfig), ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "sfb200_ar_kv_bytes": (ctypes.c_int64, [ctypes.POINTER(ArConfig)]),

@@ -5,6 +5,7 @@
 
 #include "ar_kernels.cuh"
 #include "decoder_kernels.cuh"
+#include "enc_kernels.cuh"
 
 #include <atomic>
 namespace sfb {
@@ -67,6 +68,18 @@ int sfb200_tokens_to_dense(const int64_t *tokens, const int64_t *empty_index, in
                            int64_t end_pos, int64_t end_val, void *stream) {
     if (!tokens || !empty_index || !dense) return SFB200_E_ARG;
     return launch_tokens_to_dense(tokens, empty_index, dense, B, T, cells, end_pos, end_val, as_stream(stream));
+}
+
+int64_t sfb200_encoder_workspace_bytes(int B, int T, int n_codes) { return enc_workspace_bytes(B, T, n_codes); }
+int sfb200_encode_cloud(const sfb200_enc_weights *w, const float *cloud, int B, int T, void *workspace, int64_t *raw_ind,
+                        unsigned char *mask, float *grid_feat, void *stream) {
+    return launch_encode_cloud(w, cloud, B, T, workspace, raw_ind, mask, grid_feat, as_stream(stream));
+}
+int sfb200_dense_to_tokens(const int64_t *raw_ind, const unsigned char *mask, int B, int cells, int n_codes, int max_len,
+                           int64_t end_pos, int64_t end_val, void *workspace, int64_t *dense, int64_t *tokens, int32_t *lengths,
+                           int64_t *modes, void *stream) {
+    return launch_dense_to_tokens(raw_ind, mask, B, cells, n_codes, max_len, end_pos, end_val, workspace, dense, tokens, lengths,
+                                  modes, as_stream(stream));
 }
 
 int sfb200_linear(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,

@@ -45,8 +45,33 @@ class ShapeRepresenter(nn.Module):
             model.load_state_dict(ckpt.get("state_dict", ckpt), strict=False)
         return model.eval().requires_grad_(False)
 
-    def get_indices(self, Xct, Xbd=None, stage="train", **kwargs):
-        raise NotImplementedError("point cloud -> token encoding (VQDIF encoder + quantiser) is the 'next' row §8f-1")
+    @torch.no_grad()
+    def encode_cloud(self, cloud):
+        """representers.py:68-78: cloud (B,T,3) -> (quant_feat, quant_ind, mode, sparse_unpacked (B,L,2))."""
+        vq = self.vqvae_model
+        if vq is None:
+            raise NotImplementedError("representer was built without a VQDIF (vqvae_opt)")
+        out = vq.point_encoder().quantize_cloud(cloud * self.cloud_shrinkage, max_length=self.max_length,
+                                                end_tokens=self.input_end_tokens)
+        sparse = out["c_indices"]
+        if self.no_val_ind:
+            sparse[:, :, -1] *= 0
+        return None, out["quant_ind"], out["empty_index"], sparse
+
+    @torch.no_grad()
+    def get_indices(self, Xct, Xbd=None, stage="test", **kwargs):
+        """representers.py:80-103 for inference (stage != 'train': no random conditioning masking)."""
+        if stage == "train" and self.random_cind_masking:
+            raise NotImplementedError("training-time random conditioning masking is outside the B200 hot path")
+        _, _, mode1, c_indices = self.encode_cloud(Xct)
+        z_indices = c_indices[:, :0, :] if Xbd is None else self.encode_cloud(Xbd)[3]
+        if self.uncond:
+            B, _, tn = c_indices.shape
+            c_indices = torch.tensor(list(self.input_end_tokens), dtype=torch.int64, device=c_indices.device).repeat(B, 1, 1)
+        others = dict(empty_index=mode1, origin_c_indices=c_indices, origin_z_indices=z_indices)
+        extra = self.get_extra_indices(c_indices, z_indices)
+        c_indices, z_indices = self.convert_input_indices(c_indices, z_indices)
+        return c_indices, z_indices, extra, others
 
     def get_extra_indices(self, c_indices, z_indices):
         cz = torch.cat([c_indices, z_indices], 1)

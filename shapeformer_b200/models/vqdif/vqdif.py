@@ -8,6 +8,7 @@ import torch
 import torch.nn as nn
 
 from ...decoder import ImplicitDecoder
+from ...encoder import PointEncoder
 from ...xgutils import sysutil
 
 
@@ -15,12 +16,13 @@ class VQDIF(nn.Module):
     def __init__(self, Xct_as_Xbd=False, encoder_opt=None, decoder_opt=None, quantizer_opt=None, vq_beta=1.,
                  optim_opt=None, ckpt_path=None, opt=None):
         super().__init__()
-        self.encoder = None   # LocalPoolPointnet encoder: 'next' row §8f-1
+        self.encoder = sysutil.instantiate_from_opt(encoder_opt) if encoder_opt else None
         self.decoder = sysutil.instantiate_from_opt(decoder_opt)
         self.quantizer = sysutil.instantiate_from_opt(quantizer_opt) if quantizer_opt is not None else None
         self.requires_grad_(False)
         self.eval()
         self._engine = None
+        self._point_encoder = None
         # nested loads (a parent ShapeFormer checkpoint carries representer.vqvae_model.encoder.*) go through
         # _load_from_state_dict, so the key filter and the engine invalidation are hooks, not a load_state_dict override
         self._register_load_state_dict_pre_hook(self._drop_unbuilt)
@@ -34,6 +36,7 @@ class VQDIF(nn.Module):
     @staticmethod
     def _invalidate(module, incompatible_keys):
         module._engine = None
+        module._point_encoder = None
 
     @property
     def device(self):
@@ -44,10 +47,31 @@ class VQDIF(nn.Module):
             self._engine = ImplicitDecoder(self.state_dict(), self.device)
         return self._engine
 
-    def encode(self, Xbd, **kwargs):
-        raise NotImplementedError("VQDIF encoder is the 'next' row §8f-1")
+    def point_encoder(self):
+        if self.encoder is None or self.quantizer is None:
+            raise NotImplementedError("this VQDIF was built without encoder_opt / quantizer_opt")
+        if self._point_encoder is None or self._point_encoder.device != self.device:
+            self._point_encoder = PointEncoder(self.state_dict(), self.device)
+        return self._point_encoder
 
-    quantize_cloud = encode_quant = encode
+    @torch.no_grad()
+    def encode(self, Xbd, **kwargs):
+        """vqdif.py:36-38: Xbd (B,T,3) in [-1,1] -> (grid_feat (B,128,16,16,16), grid_mask (B,16,16,16) bool)."""
+        _, mask, feat = self.point_encoder().encode_quant(Xbd, return_feat=True)
+        return feat, mask
+
+    @torch.no_grad()
+    def encode_quant(self, Xbd, **kwargs):
+        """vqdif.py:40-48 (eval): quant_feat = the selected code vectors, quant_ind, grid_mask (quant_diff is a training loss)."""
+        raw, mask = self.point_encoder().encode_quant(Xbd)
+        return dict(quant_feat=self.engine().get_code(raw), quant_ind=raw, quant_diff=None, grid_mask=mask)
+
+    @torch.no_grad()
+    def quantize_cloud(self, cloud):
+        """vqdif.py:50-58: -> (quant_ind with the batch mode in unoccupied cells, mode, encoded)."""
+        out = self.point_encoder().quantize_cloud(cloud)
+        encoded = dict(quant_feat=None, quant_ind=out["raw_ind"], quant_diff=None, grid_mask=out["mask"])
+        return out["quant_ind"], out["mode"], encoded
 
     @torch.no_grad()
     def decode(self, grid_feat, Xtg=None, **kwargs):

@@ -103,7 +103,48 @@ def vqdif_state_dict(seed=314, vq_dim=128, n_codes=4096, hidden=32):
         _, sd[f"{d}blocks.{i}.fc_1.bias"] = _lin(g, hidden, hidden)
         sd[f"{d}blocks.{i}.fc_1.weight"] = 0.1 * torch.randn(hidden, hidden, generator=g)
     sd[d + "fc_out.weight"], sd[d + "fc_out.bias"] = _lin(g, 1, hidden)
+    sd.update(encoder_state_dict(seed + 1, hidden, vq_dim))
     return sd
+
+
+def encoder_state_dict(seed=315, hidden=32, vq_dim=128, n_blocks=5):
+    """LocalPoolPointnet weights (keys as in VQDIF.state_dict(): encoder.*; shipped shapenet_res16 shapes: hidden = c_dim = 32,
+    Downsampler 32 -> 64 -> 128 in two k2s2 + k1 'crg' pairs).  Drawn from their own generator so that the decoder / codebook
+    tensors of vqdif_state_dict keep their round-1 values.  fc_1.weight (zero in the reference init) is drawn N(0, 0.1)."""
+    g = torch.Generator().manual_seed(seed)
+    e, sd = "encoder.", {}
+    sd[e + "fc_pos.weight"], sd[e + "fc_pos.bias"] = _lin(g, 2 * hidden, 3)
+    for i in range(n_blocks):
+        sd[f"{e}blocks.{i}.fc_0.weight"], sd[f"{e}blocks.{i}.fc_0.bias"] = _lin(g, hidden, 2 * hidden)
+        _, sd[f"{e}blocks.{i}.fc_1.bias"] = _lin(g, hidden, hidden)
+        sd[f"{e}blocks.{i}.fc_1.weight"] = 0.1 * torch.randn(hidden, hidden, generator=g)
+        sd[f"{e}blocks.{i}.shortcut.weight"] = _lin(g, hidden, 2 * hidden)[0]
+    sd[e + "fc_c.weight"], sd[e + "fc_c.bias"] = _lin(g, hidden, hidden)
+    ch = [hidden, 2 * hidden, 4 * hidden]
+    assert ch[-1] == vq_dim
+    for s in range(2):
+        for j, (ci, co, k) in enumerate(((ch[s], ch[s + 1], 2), (ch[s + 1], ch[s + 1], 1))):
+            pre = f"{e}downsampler.blocks.{2 * s + j}."
+            sd[pre + "conv.weight"] = _conv(g, co, ci, k)
+            sd[pre + "groupnorm.weight"] = 1 + 0.1 * torch.randn(co, generator=g)
+            sd[pre + "groupnorm.bias"] = 0.1 * torch.randn(co, generator=g)
+    return sd
+
+
+def partial_cloud(B, T=4096, seed=0):
+    """Synthetic partial scans (§8d cfg 5): T points on a random half of a noisy sphere shell inside [-0.9, 0.9]^3."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for b in range(B):
+        v = torch.randn(T, 3, generator=g)
+        v = v / v.norm(dim=1, keepdim=True)
+        n = torch.randn(3, generator=g)
+        n = n / n.norm()
+        v = torch.where((v @ n)[:, None] < 0, v - 2 * (v @ n)[:, None] * n, v)      # keep the half facing n
+        r = 0.45 + 0.3 * torch.rand(1, generator=g) + 0.02 * torch.randn(T, 1, generator=g)
+        ctr = (torch.rand(3, generator=g) - 0.5) * 0.2
+        out.append((v * r + ctr).clamp(-0.9, 0.9))
+    return torch.stack(out)
 
 
 def cond_indices(B, L_c, seed=0, n_pos=4096, n_val=4096, end_tokens=(4096, 4096), shared=False):

@@ -51,6 +51,7 @@ def test_state_dict_keys_match_the_reference():
     vq = sysutil.instantiate_from_opt(opt["pl_model_opt"])
     ref_keys = {"decoder." + k: tuple(v.shape) for k, v in dec.state_dict().items()}
     ref_keys.update({"quantizer." + k: tuple(v.shape) for k, v in q.state_dict().items()})
+    ref_keys.update({"encoder." + k: tuple(v.shape) for k, v in refutil.ref_vqdif_encoder(vsd).state_dict().items()})
     assert {k: tuple(v.shape) for k, v in vq.state_dict().items()} == ref_keys
 
 

@@ -163,3 +163,27 @@ def test_sample_indices_edge_cases_match_reference():
         for a, b in zip(rh, oh):
             fin = torch.isfinite(a)
             assert torch.equal(fin, torch.isfinite(b)) and (a[fin] - b[fin]).abs().max() < 3e-5
+
+
+def test_encoder_quantizer_and_token_packing_match_reference():
+    """§8f-1: LocalPoolPointnet + Downsampler (enc.py:66-140, torch_scatter through the scatter_reduce stand-in), Quantizer.forward
+    (quantizer.py:31-53), quantize_cloud's mode fill (vqdif.py:50-58) and batch_dense2sparse (common.py:84-122,152-169)."""
+    import importlib
+    sd = synth.vqdif_state_dict(seed=4)
+    enc = refutil.ref_vqdif_encoder(sd)
+    _, q = refutil.ref_vqdif_decoder(sd)
+    cloud = synth.partial_cloud(2, 3000, seed=1)
+    with torch.no_grad():
+        rf, rm = enc(cloud / 2.0)
+        _, _, rind, _ = q(rf)
+    of, om = O.encoder_forward(sd, cloud / 2.0)
+    assert torch.equal(rm, om) and (rf - of).abs().max() < 5e-4     # GroupNorm over mostly-empty grids amplifies fp32 noise
+    oind, _ = O.quantize(sd, rf)
+    assert torch.equal(rind, oind)
+    cm = importlib.import_module("shapeformer.models.shapeformer.common")
+    qi, mode, raw, mask = O.quantize_cloud(sd, cloud)
+    assert int(cm.pth_get_mode(raw)) == int(mode)
+    for max_length in (406, 100):
+        ru, rmode = cm.batch_dense2sparse(qi, max_length=max_length, end_tokens=torch.tensor((4096, 4096)))
+        ou, omode = O.batch_dense2sparse(qi, max_length)
+        assert torch.equal(ru, ou) and int(rmode) == int(omode)
