@@ -1,16 +1,16 @@
 // Fused implicit decoder on the tcgen05 tensor cores (the default sfb200_decoder_points path).
 //
-// One persistent CTA per SM keeps TWO 128-point tiles in flight (8 "point" warps = 2 groups x 4 warps, thread = one query
+// One persistent CTA per SM keeps THREE 128-point tiles in flight (12 "point" warps = 3 groups x 4 warps, thread = one query
 // point = one TMEM lane) plus one MMA-issuing warp.  Per tile:
-//   point warps : trilinear gather of the 32-channel feature (8 corners x 128 B from the channel-last grid)  -> split into
-//                 two TF32 parts -> tcgen05.st: the activation tile IS the A operand, living in TENSOR MEMORY
-//   MMA warp    : C5[128 x 160] = c . Wc_all^T      (all five fc_c layers in one N = 160 GEMM, 12 tcgen05.mma)
-//   then for each of the 5 ResNet blocks, two round trips
-//       point warps: tcgen05.ld accumulator -> + bias (+ fc_p / fc_c part) -> ReLU -> TF32 split -> tcgen05.st (A operand)
-//       MMA warp   : [128 x 32] = A . W^T           (12 tcgen05.mma.kind::tf32, K = 32, N = 32, weights resident in smem)
+//   point warps : trilinear gather of the 32-channel feature (8 corners x 128 B from the channel-last grid) -> tcgen05.st: the
+//                 feature vector c is the resident half of the A operand, living in TENSOR MEMORY for the whole tile
+//   11 round trips, every GEMM [128 x 32] with K = 32 or 64 (12 / 24 tcgen05.mma.kind::tf32, weights resident in smem):
+//       point warps: tcgen05.ld accumulator -> + biases -> ReLU -> TF32 hi (raw bits, truncated by the MMA) | lo -> tcgen05.st
+//       MMA warp   : D = A . W^T, serving whichever group's operand is ready (non-blocking mbarrier probes)
+//     the fc_c projection of the next block rides in the fc_1 GEMM of the current one (K concatenation [h | c])
 //   point warps : fc_out dot product, optional sigmoid, coalesced store.
 // Products are 3xTF32 (hi*hi + hi*lo + lo*hi, fp32 accumulate, chains of 12 MMAs): logits stay within ~1e-6 of the fp32
-// reference (tolerance 1e-4; single-pass TF32 misses it).  fc_p (K = 3) and fc_out (N = 1) are CUDA-core.
+// reference (tolerance 1e-4; single-pass TF32 misses it); chains of at most 24 MMAs.  fc_p (K = 3) and fc_out (N = 1) are CUDA-core.
 #include "decoder_kernels.cuh"
 #include "tc_common.cuh"
 
@@ -26,16 +26,15 @@ struct DecSmall {
 };
 __constant__ DecSmall c_dec;
 
-constexpr int DTC_THREADS = 288;          // 8 point warps + 1 MMA warp
+constexpr int DTC_G = 3;                  // point tiles in flight per CTA (one warpgroup each)
+constexpr int DTC_THREADS = DTC_G * 128 + 32;   // + 1 MMA warp
 constexpr int DTC_TILE_W = 32 * 32 * 4;   // one 32x32 fp32 weight tile (K-major SWIZZLE_128B): 4 KB
-constexpr int DTC_TILE_C = 160 * 32 * 4;  // Wc_all tile: 20 KB
-// shared memory: Wc_all hi/lo, then 10 matrices (fc_0, fc_1 per block) hi/lo
-constexpr int DTC_OFF_WC_HI = 0, DTC_OFF_WC_LO = DTC_TILE_C;
-constexpr int DTC_OFF_W = 2 * DTC_TILE_C;                       // [10][2][4 KB]
-constexpr int DTC_OFF_BAR = DTC_OFF_W + 10 * 2 * DTC_TILE_W;
-constexpr int DTC_SMEM = DTC_OFF_BAR + 64;
-// tensor memory per group (256 columns): C5 [0,160) | A hi [160,192) | A lo [192,224) | D [224,256)
-constexpr int DTC_COL_A = 160, DTC_COL_D = 224;
+// shared memory: 15 matrices (per block: fc_c, fc_0, fc_1) x (hi | lo)
+constexpr int DTC_OFF_W = 0;                                    // [15][2][4 KB]
+constexpr int DTC_OFF_BAR = DTC_OFF_W + 15 * 2 * DTC_TILE_W;
+constexpr int DTC_SMEM = DTC_OFF_BAR + 128;
+// tensor memory per group (160 columns): A hi [act 32 | c 32] | A lo [act 32 | c 32] | D 32
+constexpr int DTC_GCOLS = 160, DTC_COL_AH = 0, DTC_COL_AL = 64, DTC_COL_D = 128;
 
 // device copy of the packed MLP weights for the tile builder (filled by decoder_set_weights_tc)
 __device__ float g_dec_w[SFB200_DEC_MLP_FLOATS];
@@ -52,51 +51,66 @@ __device__ __forceinline__ float dvoxel_coord(float p, int R) {
 // write element (row, k) of a K-major SWIZZLE_128B tile (rows of 32 floats)
 __device__ __forceinline__ int sw128_index(int row, int k) { return row * 32 + ((((k >> 2) ^ (row & 7)) << 2) | (k & 3)); }
 
-// activation vector (32 fp32 in registers) -> hi | lo TF32 parts in tensor memory (A operand of the next GEMM)
-__device__ __forceinline__ void store_activation(uint32_t taddr_hi, const float (&a)[32]) {
+// activation vector (32 fp32 in registers) -> A operand in tensor memory.  hi = the raw fp32 bits: the tensor core reads only
+// the upper 19 bits of a tf32 operand (truncation, no instruction); lo = rna_tf32(a - trunc_tf32(a)), the subtraction is exact.
+__device__ __forceinline__ void store_activation(uint32_t taddr_hi, uint32_t taddr_lo, const float (&a)[32]) {
     uint32_t hi[32], lo[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) split_tf32(a[i], hi[i], lo[i]);
+    for (int i = 0; i < 32; ++i) {
+        hi[i] = __float_as_uint(a[i]);
+        lo[i] = __float_as_uint(a[i] - __uint_as_float(hi[i] & 0xFFFFE000u)) + 0x1000u;
+    }
     tmem_st32(taddr_hi, hi);
-    tmem_st32(taddr_hi + 32, lo);
+    tmem_st32(taddr_lo, lo);
     tmem_st_wait();
 }
 
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// One persistent CTA per SM keeps THREE 128-point tiles in flight (3 warpgroups of point threads + 1 MMA warp).  Per tile
+// (thread = query point = TMEM lane), 11 tensor-core round trips, all K = 32 / 64, N = 32, 3xTF32:
+//   init   D = c . Wc[0]^T                                    net = fc_p(p) + D + bc[0]
+//   blk b  D = relu(net) . W0[b]^T                            h = relu(D + b0[b])
+//          D = [h | c] . [W1[b] | Wc[b+1]]^T  (K = 64)        net += D + b1[b] + bc[b+1]        (last block: K = 32, no fc_c)
+// i.e. the fc_c projection of the NEXT block rides in the fc_1 GEMM of the current one (K concatenation): the feature vector c
+// stays resident in tensor memory for the whole tile and no 160-column side accumulator is needed, so three tiles fit in TMEM.
 __global__ void __launch_bounds__(DTC_THREADS, 1)
 decoder_points_tc_kernel(const float *__restrict__ grid, const float *__restrict__ xtg, int64_t xtg_bstride,
                          float *__restrict__ out, int B, int R, int64_t N, int sigmoid) {
     extern __shared__ __align__(1024) unsigned char dsm[];
-    uint64_t *ready = reinterpret_cast<uint64_t *>(dsm + DTC_OFF_BAR);   // [2] activation tile of group g is in TMEM
-    uint64_t *done = ready + 2;                                           // [2] GEMM for group g finished
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 2);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t *ready = reinterpret_cast<uint64_t *>(dsm + DTC_OFF_BAR);   // [G] A operand of group g is in TMEM
+    uint64_t *done = ready + DTC_G;                                       // [G] GEMM for group g finished
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + DTC_G);
+    const int tid = threadIdx.x, warp = tid >> 5;
 
-    // ---- one-time: weights -> TF32 hi/lo swizzled tiles in shared memory
-    {
-        float *wc_hi = reinterpret_cast<float *>(dsm + DTC_OFF_WC_HI), *wc_lo = reinterpret_cast<float *>(dsm + DTC_OFF_WC_LO);
-        // packed layout (decoder.py::pack_mlp_weights): fc_p (96+32), per block [fc_c W 1024, b 32, fc_0 W, b, fc_1 W, b], fc_out
-        for (int e = tid; e < 5 * 1024; e += DTC_THREADS) {
-            const int blk = e >> 10, o = (e >> 5) & 31, i = e & 31;
-            uint32_t h, l;
-            split_tf32(g_dec_w[128 + blk * 3168 + o * 32 + i], h, l);
-            const int idx = sw128_index(blk * 32 + o, i);
-            wc_hi[idx] = __uint_as_float(h); wc_lo[idx] = __uint_as_float(l);
-        }
-        for (int e = tid; e < 10 * 1024; e += DTC_THREADS) {
-            const int mtx = e >> 10, blk = mtx >> 1, which = mtx & 1, o = (e >> 5) & 31, i = e & 31;
-            uint32_t h, l;
-            split_tf32(g_dec_w[128 + blk * 3168 + 1056 * (1 + which) + o * 32 + i], h, l);
-            float *t_hi = reinterpret_cast<float *>(dsm + DTC_OFF_W + (mtx * 2) * DTC_TILE_W);
-            float *t_lo = reinterpret_cast<float *>(dsm + DTC_OFF_W + (mtx * 2 + 1) * DTC_TILE_W);
-            const int idx = sw128_index(o, i);
-            t_hi[idx] = __uint_as_float(h); t_lo[idx] = __uint_as_float(l);
-        }
+    // ---- one-time: weights -> TF32 hi/lo swizzled tiles in shared memory.  Matrix m = blk * 3 + {0: fc_c, 1: fc_0, 2: fc_1}
+    // packed layout (decoder.py::pack_mlp_weights): fc_p (96+32), per block [fc_c W 1024, b 32, fc_0 W, b, fc_1 W, b], fc_out
+    for (int e = tid; e < 15 * 1024; e += DTC_THREADS) {
+        const int mtx = e >> 10, blk = mtx / 3, which = mtx % 3, o = (e >> 5) & 31, i = e & 31;
+        uint32_t h, l;
+        split_tf32(g_dec_w[128 + blk * 3168 + 1056 * which + o * 32 + i], h, l);
+        float *t_hi = reinterpret_cast<float *>(dsm + DTC_OFF_W + (mtx * 2) * DTC_TILE_W);
+        float *t_lo = reinterpret_cast<float *>(dsm + DTC_OFF_W + (mtx * 2 + 1) * DTC_TILE_W);
+        const int idx = sw128_index(o, i);
+        t_hi[idx] = __uint_as_float(h); t_lo[idx] = __uint_as_float(l);
     }
     if (tid == 0) {
-        for (int g = 0; g < 2; ++g) { mbar_init(&ready[g], 128); mbar_init(&done[g], 1); }
+        for (int g = 0; g < DTC_G; ++g) { mbar_init(&ready[g], 4); mbar_init(&done[g], 1); }
         mbar_fence_init();
     }
-    if (warp == 8) tmem_alloc<512>(tmem_slot);
+    if (warp == DTC_G * 4) tmem_alloc<512>(tmem_slot);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -105,16 +119,16 @@ decoder_points_tc_kernel(const float *__restrict__ grid, const float *__restrict
 
     const int64_t tiles_per_shape = (N + 127) / 128;
     const int64_t n_tiles = tiles_per_shape * B;
-    const int64_t stride = (int64_t)gridDim.x * 2;
+    const int64_t stride = (int64_t)gridDim.x * DTC_G;
 
-    if (warp < 8) {
+    if (warp < DTC_G * 4) {
         // =========================================== point warps ===========================================
-        const int g = warp >> 2;
-        const uint32_t tg = tmem_base + g * 256 + ((uint32_t)(32 * (warp & 3)) << 16);
+        const int g = warp >> 2, lane = tid & 31;
+        const uint32_t tg = tmem_base + g * DTC_GCOLS + ((uint32_t)(32 * (warp & 3)) << 16);
         uint32_t ph_done = 0;   // number of completed GEMM phases for this group
         auto wait_gemm = [&]() { mbar_wait(&done[g], ph_done & 1); ++ph_done; tc_fence_after(); };
-        auto signal = [&]() { tc_fence_before(); mbar_arrive(&ready[g]); };
-        for (int64_t tile = (int64_t)blockIdx.x * 2 + g; tile < n_tiles; tile += stride) {
+        auto signal = [&]() { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&ready[g]); };
+        for (int64_t tile = (int64_t)blockIdx.x * DTC_G + g; tile < n_tiles; tile += stride) {
             const int b = (int)(tile / tiles_per_shape);
             const int64_t n = (tile % tiles_per_shape) * 128 + (tid & 127);
             const bool valid = n < N;
@@ -123,7 +137,7 @@ decoder_points_tc_kernel(const float *__restrict__ grid, const float *__restrict
             const float px = pt[0] * 0.5f, py = pt[1] * 0.5f, pz = pt[2] * 0.5f;   // VQDIF.decode: Xtg / 2
             float net[32];
             {
-                // ---- trilinear feature (vqdif/dec.py:62-68), written to TMEM as the first A operand
+                // ---- trilinear feature (vqdif/dec.py:62-68) -> the resident c half of the A operand
                 const float fx = dvoxel_coord(px, R), fy = dvoxel_coord(py, R), fz = dvoxel_coord(pz, R);
                 const float x0f = floorf(fx), y0f = floorf(fy), z0f = floorf(fz);
                 const int x0 = (int)x0f, y0 = (int)y0f, z0 = (int)z0f;
@@ -152,9 +166,9 @@ decoder_points_tc_kernel(const float *__restrict__ grid, const float *__restrict
                                 c[4 * q + 3] = fmaf(w, v.w, c[4 * q + 3]);
                             }
                         }
-                store_activation(tg + DTC_COL_A, c);
+                store_activation(tg + DTC_COL_AH + 32, tg + DTC_COL_AL + 32, c);
             }
-            signal();                                   // -> GEMM0: C5 = c . Wc_all^T
+            signal();                                   // -> init: D = c . Wc[0]^T
             // net = fc_p(p) while the tensor core works
 #pragma unroll
             for (int o = 0; o < 32; ++o) {
@@ -169,88 +183,106 @@ decoder_points_tc_kernel(const float *__restrict__ grid, const float *__restrict
             for (int blk = 0; blk < 5; ++blk) {
                 uint32_t v[32];
                 float a[32];
-                // net += fc_c[blk](c)          (column slice blk of C5)
-                tmem_ld32(tg + blk * 32, v);
+                // net += (fc_c[blk](c), and for blk > 0 also fc_1[blk-1](h)) + biases; A <- relu(net)
+                tmem_ld32(tg + DTC_COL_D, v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    net[i] += __uint_as_float(v[i]) + c_dec.bc[blk][i];
+                    float add = __uint_as_float(v[i]) + c_dec.bc[blk][i];
+                    if (blk > 0) add += c_dec.b1[blk - 1][i];
+                    net[i] += add;
                     a[i] = fmaxf(net[i], 0.f);
                 }
-                store_activation(tg + DTC_COL_A, a);
+                store_activation(tg + DTC_COL_AH, tg + DTC_COL_AL, a);
                 signal();                               // -> D = relu(net) . fc_0^T
                 wait_gemm();
                 tmem_ld32(tg + DTC_COL_D, v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 32; ++i) a[i] = fmaxf(__uint_as_float(v[i]) + c_dec.b0[blk][i], 0.f);
-                store_activation(tg + DTC_COL_A, a);
-                signal();                               // -> D = relu(h) . fc_1^T
+                store_activation(tg + DTC_COL_AH, tg + DTC_COL_AL, a);
+                signal();                               // -> D = [h | c] . [fc_1 | fc_c[blk+1]]^T
                 wait_gemm();
+            }
+            {
+                uint32_t v[32];
                 tmem_ld32(tg + DTC_COL_D, v);
                 tmem_ld_wait();
+                float o = c_dec.bo;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) net[i] += __uint_as_float(v[i]) + c_dec.b1[blk][i];
+                for (int i = 0; i < 32; ++i) {
+                    const float r = net[i] + (__uint_as_float(v[i]) + c_dec.b1[4][i]);
+                    o = fmaf(c_dec.wo[i], fmaxf(r, 0.f), o);
+                }
+                if (sigmoid) o = 1.0f / (1.0f + expf(-o));
+                if (valid) out[(size_t)b * N + n] = o;
             }
-            float o = c_dec.bo;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o = fmaf(c_dec.wo[i], fmaxf(net[i], 0.f), o);
-            if (sigmoid) o = 1.0f / (1.0f + expf(-o));
-            if (valid) out[(size_t)b * N + n] = o;
         }
         tc_fence_before();
     } else {
         // =========================================== MMA issuer ===========================================
-        // the whole warp stays converged and one elected lane issues: descriptors live in uniform registers (tc_common.cuh)
-        constexpr uint32_t IDESC160 = instr_desc(2, 128, 160), IDESC32 = instr_desc(2, 128, 32);
-        const uint32_t wc_hi = smem_u32(dsm + DTC_OFF_WC_HI), wc_lo = smem_u32(dsm + DTC_OFF_WC_LO);
+        // the whole warp stays converged and one elected lane issues (tc_common.cuh); the three groups are served in whatever
+        // order their operands become ready (non-blocking mbarrier probes)
+        constexpr uint32_t IDESC32 = instr_desc(2, 128, 32);
         const uint32_t w0 = smem_u32(dsm + DTC_OFF_W);
-        uint32_t ph[2] = {0, 0};
-        for (int64_t base = (int64_t)blockIdx.x * 2; base < n_tiles; base += stride) {
-            const bool has[2] = {base < n_tiles, base + 1 < n_tiles};
-            for (int step = 0; step < 11; ++step) {
+        uint32_t ph[DTC_G], step[DTC_G];
+        int64_t next_tile[DTC_G];
+        int live = 0;
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    if (!has[g]) continue;
-                    mbar_wait(&ready[g], ph[g] & 1);
-                    ++ph[g];
-                    tc_fence_after();
-                    const uint32_t tgb = tmem_base + g * 256;
-                    const uint32_t a_hi = tgb + DTC_COL_A, a_lo = a_hi + 32;
-                    if (step == 0) {
-                        const uint64_t bh = smem_desc_k128(wc_hi), bl = smem_desc_k128(wc_lo);
-                        if (elect_one()) {
+        for (int g = 0; g < DTC_G; ++g) {
+            ph[g] = 0; step[g] = 0;
+            next_tile[g] = (int64_t)blockIdx.x * DTC_G + g;
+            live += next_tile[g] < n_tiles;
+        }
+        while (live > 0) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                mma_tf32_ts(tgb, a_lo + 8 * k, bh + 2 * k, IDESC160, k != 0);
-                                mma_tf32_ts(tgb, a_hi + 8 * k, bl + 2 * k, IDESC160, 1);
-                                mma_tf32_ts(tgb, a_hi + 8 * k, bh + 2 * k, IDESC160, 1);
-                            }
-                            mma_commit(&done[g]);
-                        }
-                    } else {
-                        const int mtx = step - 1;   // (blk, fc_0 / fc_1)
-                        const uint64_t bh = smem_desc_k128(w0 + (mtx * 2) * DTC_TILE_W);
-                        const uint64_t bl = smem_desc_k128(w0 + (mtx * 2 + 1) * DTC_TILE_W);
-                        const uint32_t d = tgb + DTC_COL_D;
-                        if (elect_one()) {
+            for (int g = 0; g < DTC_G; ++g) {
+                if (next_tile[g] >= n_tiles) continue;
+                if (!mbar_test(&ready[g], ph[g] & 1)) continue;
+                ++ph[g];
+                tc_fence_after();
+                const uint32_t tgb = tmem_base + g * DTC_GCOLS;
+                const uint32_t d = tgb + DTC_COL_D;
+                const uint32_t st = step[g];
+                // step 0: c . Wc[0]; odd steps 2b+1: act . W0[b]; even steps 2b+2: act . W1[b] (+ c . Wc[b+1] for b < 4)
+                const int blk = st == 0 ? 0 : (int)(st - 1) >> 1;
+                const int mtx = st == 0 ? 0 : ((st & 1) ? blk * 3 + 1 : blk * 3 + 2);
+                const uint32_t a_off = st == 0 ? 32u : 0u;      // the c half for the init step
+                const bool concat = st != 0 && (st & 1) == 0 && blk < 4;
+                const uint64_t bh = smem_desc_k128(w0 + (mtx * 2) * DTC_TILE_W), bl = smem_desc_k128(w0 + (mtx * 2 + 1) * DTC_TILE_W);
+                const uint64_t ch = smem_desc_k128(w0 + ((blk + 1) * 3 * 2) * DTC_TILE_W);
+                const uint64_t cl = smem_desc_k128(w0 + ((blk + 1) * 3 * 2 + 1) * DTC_TILE_W);
+                if (elect_one()) {
+                    const uint32_t a_hi = tgb + DTC_COL_AH + a_off, a_lo = tgb + DTC_COL_AL + a_off;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                mma_tf32_ts(d, a_lo + 8 * k, bh + 2 * k, IDESC32, k != 0);
-                                mma_tf32_ts(d, a_hi + 8 * k, bl + 2 * k, IDESC32, 1);
-                                mma_tf32_ts(d, a_hi + 8 * k, bh + 2 * k, IDESC32, 1);
-                            }
-                            mma_commit(&done[g]);
+                    for (int k = 0; k < 4; ++k) {
+                        mma_tf32_ts(d, a_lo + 8 * k, bh + 2 * k, IDESC32, k != 0);
+                        mma_tf32_ts(d, a_hi + 8 * k, bl + 2 * k, IDESC32, 1);
+                        mma_tf32_ts(d, a_hi + 8 * k, bh + 2 * k, IDESC32, 1);
+                    }
+                    if (concat) {
+                        const uint32_t c_hi = tgb + DTC_COL_AH + 32, c_lo = tgb + DTC_COL_AL + 32;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            mma_tf32_ts(d, c_lo + 8 * k, ch + 2 * k, IDESC32, 1);
+                            mma_tf32_ts(d, c_hi + 8 * k, cl + 2 * k, IDESC32, 1);
+                            mma_tf32_ts(d, c_hi + 8 * k, ch + 2 * k, IDESC32, 1);
                         }
                     }
-                    __syncwarp();
+                    mma_commit(&done[g]);
+                }
+                __syncwarp();
+                if (++step[g] == 11) {
+                    step[g] = 0;
+                    next_tile[g] += stride;
+                    if (next_tile[g] >= n_tiles) --live;
                 }
             }
         }
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 8) {
+    if (warp == DTC_G * 4) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
