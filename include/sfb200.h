@@ -184,6 +184,21 @@ void sfb200_ar_destroy(sfb200_ar *h);
  * TF32 tiles of every block / head weight.  Decode steps with 9..64 rows then use sfb200_linear_tc_ps. */
 int sfb200_ar_set_pretiled(sfb200_ar *h, float *pretiled, void *stream);
 
+/* Optional: bind a caller-owned buffer of sfb200_ar_weight_floats(cfg) floats and fill it (on `stream`) with the LOW parts of
+ * the two-term TF32 split of the weight blob (same layout).  Every nn.Linear over more than 64 rows (prefill, decode batches
+ * of > 64 rows) then runs the TMA-fed tensor-core kernel of csrc/tc_big.cu, which reads both parts of both operands from
+ * memory (Block.forward / heads, transformer/mingpt.py:74-111,222-231). */
+int sfb200_ar_set_lo_weights(sfb200_ar *h, float *lo_blob, void *stream);
+
+/* y = act(x W^T + bias) + residual with that kernel (any M; x_lo / W_lo = low parts as produced by sfb200_split_lo; y_lo
+ * optional output = low part of y; partial: sfb200_big_partial_floats() floats, counters: 1024 zeroed int32, both may be NULL
+ * = no split-K).  act: 0 none, 1 exact-erf GELU. */
+int64_t sfb200_big_partial_floats(void);
+int sfb200_split_lo(const float *x, float *lo, int64_t n, void *stream);
+int sfb200_linear_big(const float *x, const float *x_lo, const float *W, const float *W_lo, const float *bias,
+                      const float *residual, float *y, float *y_lo, int M, int N, int K, int act, float *partial,
+                      int32_t *counters, void *stream);
+
 typedef struct sfb200_ar_sampling {
     int top_k;                    /* <= 0 disables (common.py:265) */
     float top_p;                  /* <= 0 disables (common.py:271) */

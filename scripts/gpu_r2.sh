@@ -17,7 +17,7 @@ for st in $STAGES; do
       timeout 900 python bench.py --steps ${BENCH_STEPS:-3} --warmup 3 ${BENCH_ARGS} > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "== bench rc=$?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err ;;
     ncu_attn)
       # the decode attention kernel at position ~512 of the benchmarked batch (64 rows, groups of 4): skip 256 steps x 24 launches
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_decode -s 6144 -c 2 -f -o gpurun_out/attn_decode_r2 \
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_grouped -s 6144 -c 2 -f -o gpurun_out/attn_grouped_r2 \
         python bench.py --steps 1 --warmup 0 --ar-steps 258 --no-e2e --no-cpu-baseline --graph off --no-roofline > gpurun_out/p_attn.log 2>&1; echo "== ncu_attn rc=$?" ;;
     ncu_dec)
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:decoder_points_tc -c 1 -f -o gpurun_out/decoder_tc_r2 \

@@ -4,7 +4,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsfb200.so")
+# SFB200_LIB: development override (e.g. the timeline-probe build of scripts/build_probe.sh)
+LIB_PATH = os.environ.get("SFB200_LIB") or os.path.join(_HERE, "lib", "libsfb200.so")
 
 c_i64p = ctypes.POINTER(ctypes.c_int64)
 c_f32p = ctypes.POINTER(ctypes.c_float)
@@ -72,6 +73,11 @@ SIGNATURES = {
     "sfb200_ar_history_floats": (ctypes.c_int64, [ctypes.POINTER(ArConfig)]),
     "sfb200_ar_pretiled_floats": (ctypes.c_int64, [ctypes.POINTER(ArConfig)]),
     "sfb200_ar_set_pretiled": (ctypes.c_int, [vp, vp, vp]),
+    "sfb200_ar_set_lo_weights": (ctypes.c_int, [vp, vp, vp]),
+    "sfb200_big_partial_floats": (ctypes.c_int64, []),
+    "sfb200_split_lo": (ctypes.c_int, [vp, vp, ctypes.c_int64, vp]),
+    "sfb200_linear_big": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         vp, vp, vp]),
     "sfb200_ar_create": (ctypes.c_int, [ctypes.POINTER(ArConfig), vp, vp, vp, vp, vp, ctypes.POINTER(vp)]),
     "sfb200_ar_destroy": (None, [vp]),
     "sfb200_ar_begin": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ArSampling), vp]),

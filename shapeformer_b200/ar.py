@@ -127,6 +127,21 @@ class ARSampler:
             _lib.check(self.lib.sfb200_ar_set_pretiled(self.handle, _lib.ptr(self.pretiled), _lib.stream_ptr()),
                        "sfb200_ar_set_pretiled")
 
+        # GEMMs over more than 64 rows (prefill of >= 1 shape, decode batches of > 64 rows) run the TMA-fed kernel of
+        # csrc/tc_big.cu, which reads the low parts of the TF32 operand split from memory: one extra copy of the weight blob,
+        # shared by every sampler built on the same packed weights (SFB200_BIG=0 keeps the in-kernel-split GEMM)
+        self.weights_lo = None
+        if os.environ.get("SFB200_BIG", "1")[:1] != "0":
+            lo = getattr(self.weights, "_sfb200_lo", None)
+            if lo is None:
+                lo = torch.empty_like(self.weights)
+                try:
+                    self.weights._sfb200_lo = lo
+                except Exception:
+                    pass
+            self.weights_lo = lo
+            _lib.check(self.lib.sfb200_ar_set_lo_weights(self.handle, _lib.ptr(lo), _lib.stream_ptr()), "sfb200_ar_set_lo_weights")
+
     def __del__(self):
         try:
             if getattr(self, "handle", None):

@@ -78,6 +78,8 @@ struct Buffers {   // byte offsets into the workspace
     int64_t logp;                           // (max_rows, max_steps, 2) log-probabilities of the sampled tokens
     int64_t att_cnt;                        // grouped attention: arrival counters per (row, head)
     int64_t ch_bar, ch_stats, ch_scratch;   // GEMM-chain kernel: barrier counters, LayerNorm row statistics, split-K partials
+    // large-M GEMM (tc_big.cu): lo parts of the GEMM input activations (decode: h, att, ff; prefill: ph, pff), split-K scratch
+    int64_t h_lo, att_lo, ff_lo, ph_lo, pff_lo, bg_part, bg_cnt;
     int64_t total;
 };
 
@@ -117,6 +119,13 @@ static void carve(const sfb200_ar_config *c, Buffers *b) {
     b->ch_bar = take((CH_MAX_BARRIERS + 1) * 4);
     b->ch_stats = take(64 * ((d + 127) / 128) * 2 * F);
     b->ch_scratch = take((int64_t)chain_scratch_floats(CHAIN_MAX_GRID) * F);
+    b->h_lo = take(B * d * F);
+    b->att_lo = take(B * d * F);
+    b->ff_lo = take(B * 4 * d * F);
+    b->ph_lo = take(P * d * F);
+    b->pff_lo = take(P * 4 * d * F);
+    b->bg_part = take((int64_t)big_partial_floats() * F);
+    b->bg_cnt = take(BG_MAX_TILES * 4);
     b->total = o;
 }
 
@@ -130,6 +139,8 @@ struct sfb200_ar {
     Buffers buf;
     const float *w;
     float *wt;                 // optional pre-split GEMM weight tiles (sfb200_ar_set_pretiled)
+    const float *wlo;          // optional lo parts of the weight blob, same layout (sfb200_ar_set_lo_weights): GEMMs over more
+                               // than 64 rows (large decode batches, prefill) then run the TMA-fed tc_big kernel
     char *ws;
     float *kv;
     int64_t *tokens;
@@ -291,8 +302,13 @@ static int64_t wt_offset(const sfb200_ar_config *c, int id, int g, int l) {
 
 // nn.Linear dispatch: 9..64 rows -> tcgen05 3xTF32 from pre-split tiles (when bound), else tcgen05 with in-kernel split;
 // <= 8 rows -> GEMV / FFMA kernels on the fp32 weights.
+static inline bool big_path(const sfb200_ar *h, int M) { return h->wlo != nullptr && M > 64; }
+
 static int linear(sfb200_ar *h, int wid, int g, int l, const float *x, const float *bias, const float *residual, float *y,
-                  int M, int N, int K, int act, cudaStream_t s) {
+                  int M, int N, int K, int act, cudaStream_t s, const float *x_lo = nullptr, float *y_lo = nullptr) {
+    if (big_path(h, M) && x_lo)
+        return launch_linear_big(x, x_lo, W_(h, wid, g, l), h->wlo + weight_offset(&h->lay, wid, g, l), bias, residual, y, y_lo, M, N,
+                                 K, act, WS_<float>(h, h->buf.bg_part), WS_<int>(h, h->buf.bg_cnt), s);
     if (M >= 9 && M <= 64 && h->wt)
         return launch_linear_tc_ps(x, h->wt + wt_offset(&h->cfg, wid, g, l), bias, residual, y, M, N, K, act, s);
     const float *W = W_(h, wid, g, l);
@@ -305,15 +321,20 @@ static int block_prefill(sfb200_ar *h, int g, int l, float *x, int row0, int row
                          const int32_t *rowmap) {
     const int d = h->cfg.n_embd, H = h->cfg.n_head, M = rows * T;
     float *ph = WS_<float>(h, h->buf.ph), *pqkv = WS_<float>(h, h->buf.pqkv), *pff = WS_<float>(h, h->buf.pff);
-    SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN1_W, g, l), W_(h, SFB200_W_LN1_B, g, l), ph, M, d, s));
-    SFB_TRY(linear(h, SFB200_W_QKV_W, g, l, ph, W_(h, SFB200_W_QKV_B, g, l), nullptr, pqkv, M, 3 * d, d, 0, s));
+    // tc_big GEMMs read the lo parts of their input activations from memory: written by the producing kernel where that is
+    // one of ours with an epilogue (LayerNorm, GEMM), by split_lo for the attention output
+    const bool big = big_path(h, M);
+    float *ph_lo = big ? WS_<float>(h, h->buf.ph_lo) : nullptr, *pff_lo = big ? WS_<float>(h, h->buf.pff_lo) : nullptr;
+    SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN1_W, g, l), W_(h, SFB200_W_LN1_B, g, l), ph, M, d, s, ph_lo));
+    SFB_TRY(linear(h, SFB200_W_QKV_W, g, l, ph, W_(h, SFB200_W_QKV_B, g, l), nullptr, pqkv, M, 3 * d, d, 0, s, ph_lo));
     // with a rowmap the cache rows are rowmap[i] (cache base = row 0), otherwise rows row0 .. row0+rows-1
     SFB_TRY(launch_attn_prefill(pqkv, kcache(h, g, l, rowmap ? 0 : row0), vcache(h, g, l, rowmap ? 0 : row0), ph, rows, H, T,
                                 h->cfg.max_len, s, rowmap));
-    SFB_TRY(linear(h, SFB200_W_PROJ_W, g, l, ph, W_(h, SFB200_W_PROJ_B, g, l), x, x, M, d, d, 0, s));
-    SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN2_W, g, l), W_(h, SFB200_W_LN2_B, g, l), ph, M, d, s));
-    SFB_TRY(linear(h, SFB200_W_FC1_W, g, l, ph, W_(h, SFB200_W_FC1_B, g, l), nullptr, pff, M, 4 * d, d, 1, s));
-    SFB_TRY(linear(h, SFB200_W_FC2_W, g, l, pff, W_(h, SFB200_W_FC2_B, g, l), x, x, M, d, 4 * d, 0, s));
+    if (big) SFB_TRY(launch_split_lo(ph, ph_lo, (size_t)M * d, s));
+    SFB_TRY(linear(h, SFB200_W_PROJ_W, g, l, ph, W_(h, SFB200_W_PROJ_B, g, l), x, x, M, d, d, 0, s, ph_lo));
+    SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN2_W, g, l), W_(h, SFB200_W_LN2_B, g, l), ph, M, d, s, ph_lo));
+    SFB_TRY(linear(h, SFB200_W_FC1_W, g, l, ph, W_(h, SFB200_W_FC1_B, g, l), nullptr, pff, M, 4 * d, d, 1, s, ph_lo, pff_lo));
+    SFB_TRY(linear(h, SFB200_W_FC2_W, g, l, pff, W_(h, SFB200_W_FC2_B, g, l), x, x, M, d, 4 * d, 0, s, pff_lo));
     return SFB200_OK;
 }
 
@@ -361,13 +382,17 @@ static int block_step(sfb200_ar *h, int g, int l, float *x, cudaStream_t s) {
     const int d = h->cfg.n_embd, B = h->B;
     float *hb = WS_<float>(h, h->buf.h), *qkv = WS_<float>(h, h->buf.qkv), *att = WS_<float>(h, h->buf.att);
     float *ff = WS_<float>(h, h->buf.ff);
-    SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN1_W, g, l), W_(h, SFB200_W_LN1_B, g, l), hb, B, d, s));
-    SFB_TRY(linear(h, SFB200_W_QKV_W, g, l, hb, W_(h, SFB200_W_QKV_B, g, l), nullptr, qkv, B, 3 * d, d, 0, s));
+    const bool big = big_path(h, B);
+    float *h_lo = big ? WS_<float>(h, h->buf.h_lo) : nullptr, *att_lo = big ? WS_<float>(h, h->buf.att_lo) : nullptr;
+    float *ff_lo = big ? WS_<float>(h, h->buf.ff_lo) : nullptr;
+    SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN1_W, g, l), W_(h, SFB200_W_LN1_B, g, l), hb, B, d, s, h_lo));
+    SFB_TRY(linear(h, SFB200_W_QKV_W, g, l, hb, W_(h, SFB200_W_QKV_B, g, l), nullptr, qkv, B, 3 * d, d, 0, s, h_lo));
     SFB_TRY(attn_step(h, g, l, s));
-    SFB_TRY(linear(h, SFB200_W_PROJ_W, g, l, att, W_(h, SFB200_W_PROJ_B, g, l), x, x, B, d, d, 0, s));
-    SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN2_W, g, l), W_(h, SFB200_W_LN2_B, g, l), hb, B, d, s));
-    SFB_TRY(linear(h, SFB200_W_FC1_W, g, l, hb, W_(h, SFB200_W_FC1_B, g, l), nullptr, ff, B, 4 * d, d, 1, s));
-    SFB_TRY(linear(h, SFB200_W_FC2_W, g, l, ff, W_(h, SFB200_W_FC2_B, g, l), x, x, B, d, 4 * d, 0, s));
+    if (big) SFB_TRY(launch_split_lo(att, att_lo, (size_t)B * d, s));
+    SFB_TRY(linear(h, SFB200_W_PROJ_W, g, l, att, W_(h, SFB200_W_PROJ_B, g, l), x, x, B, d, d, 0, s, att_lo));
+    SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN2_W, g, l), W_(h, SFB200_W_LN2_B, g, l), hb, B, d, s, h_lo));
+    SFB_TRY(linear(h, SFB200_W_FC1_W, g, l, hb, W_(h, SFB200_W_FC1_B, g, l), nullptr, ff, B, 4 * d, d, 1, s, h_lo, ff_lo));
+    SFB_TRY(linear(h, SFB200_W_FC2_W, g, l, ff, W_(h, SFB200_W_FC2_B, g, l), x, x, B, d, 4 * d, 0, s, ff_lo));
     return SFB200_OK;
 }
 
@@ -461,8 +486,9 @@ static int group_step(sfb200_ar *h, int g, float *x, float *logits, cudaStream_t
 static int head(sfb200_ar *h, int g, const float *x, float *logits, int rows, cudaStream_t s) {
     const int d = h->cfg.n_embd;
     float *hb = WS_<float>(h, h->buf.h);
-    SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_HEAD_LN_W, g, 0), W_(h, SFB200_W_HEAD_LN_B, g, 0), hb, rows, d, s));
-    SFB_TRY(linear(h, SFB200_W_HEAD_W, g, 0, hb, nullptr, nullptr, logits, rows, h->cfg.vocab[g], d, 0, s));
+    float *h_lo = big_path(h, rows) ? WS_<float>(h, h->buf.h_lo) : nullptr;
+    SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_HEAD_LN_W, g, 0), W_(h, SFB200_W_HEAD_LN_B, g, 0), hb, rows, d, s, h_lo));
+    SFB_TRY(linear(h, SFB200_W_HEAD_W, g, 0, hb, nullptr, nullptr, logits, rows, h->cfg.vocab[g], d, 0, s, h_lo));
     return SFB200_OK;
 }
 
@@ -485,6 +511,7 @@ extern "C" int sfb200_ar_begin_shared(sfb200_ar *h, int B, int L_cond, const sfb
     int32_t *st = WS_<int32_t>(h, h->buf.st);
     SFB_TRY(launch_state_init(st, L_cond, s));
     SFB_CUDA_TRY(cudaMemsetAsync(WS_<int>(h, h->buf.att_cnt), 0, (size_t)h->cfg.max_rows * h->cfg.n_head * 4, s));
+    SFB_CUDA_TRY(cudaMemsetAsync(WS_<int>(h, h->buf.bg_cnt), 0, BG_MAX_TILES * 4, s));
     if (chain_active(h)) {
         SFB_TRY(chain_build_maps(h));
         SFB_CUDA_TRY(cudaMemsetAsync(WS_<unsigned int>(h, h->buf.ch_bar), 0, (CH_MAX_BARRIERS + 1) * 4, s));
@@ -670,6 +697,14 @@ extern "C" int64_t sfb200_ar_pretiled_floats(const sfb200_ar_config *cfg) {
     const int d = cfg->n_embd;
     return (int64_t)(cfg->n_layers[0] + cfg->n_layers[1]) * wt_block_floats(cfg) + tc_pretiled_floats(cfg->vocab[0], d) +
            tc_pretiled_floats(cfg->vocab[1], d);
+}
+
+extern "C" int sfb200_ar_set_lo_weights(sfb200_ar *h, float *lo_blob, void *stream) {
+    if (!h || !lo_blob) return SFB200_E_ARG;
+    SFB_TRY(launch_split_lo(h->w, lo_blob, (size_t)h->lay.total, as_stream(stream)));
+    h->wlo = lo_blob;
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }   // the captured step used the other kernels
+    return SFB200_OK;
 }
 
 extern "C" int sfb200_ar_set_pretiled(sfb200_ar *h, float *pretiled, void *stream) {

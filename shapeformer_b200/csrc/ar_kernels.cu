@@ -147,7 +147,7 @@ __global__ void ar_take_last_kernel(const float *x, float *out, int d, int T, co
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float *x, const float *__restrict__ w,
                                                         const float *__restrict__ bvec, float *y, int rows,
-                                                        int d) {
+                                                        int d, float *y_lo) {
     pdl_trigger();
     pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -180,6 +180,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *x, const fl
             r.z = (v[j].z - mean) * rstd * g.z + bb.z;
             r.w = (v[j].w - mean) * rstd * g.w + bb.w;
             st4(yr + i, r);
+            // lo part of the TF32 split (hi = hardware truncation) for a tc_big GEMM consumer
+            if (y_lo) st4(y_lo + (size_t)warp * d + i, make_float4(tf32_lo(r.x), tf32_lo(r.y), tf32_lo(r.z), tf32_lo(r.w)));
         }
         return;
     }
@@ -203,6 +205,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *x, const fl
         r.z = (v.z - mean) * rstd * g.z + bb.z;
         r.w = (v.w - mean) * rstd * g.w + bb.w;
         st4(yr + i, r);
+        if (y_lo) st4(y_lo + (size_t)warp * d + i, make_float4(tf32_lo(r.x), tf32_lo(r.y), tf32_lo(r.z), tf32_lo(r.w)));
     }
 }
 
@@ -1051,13 +1054,13 @@ int launch_add_target(const float *x_in, float *x_out, const int64_t *tokens, co
 int launch_take_last(const float *x, float *out, int B, int d, int T, cudaStream_t s, const int32_t *rowmap) {
     return launch_ex("ar_take_last", ar_take_last_kernel, dim3(B), dim3(256), 0, s, dim3(1, 1, 1), x, out, d, T, rowmap);
 }
-int launch_layernorm(const float *x, const float *w, const float *b, float *y, int rows, int d, cudaStream_t s) {
+int launch_layernorm(const float *x, const float *w, const float *b, float *y, int rows, int d, cudaStream_t s, float *y_lo) {
     if (rows <= 0) return SFB200_OK;
     if (d % 4 != 0) return SFB200_E_ARG;
     const dim3 grid((rows + 7) / 8);
-    if (d == 1024) return launch_ex("layernorm", layernorm_kernel<8>, grid, dim3(256), 0, s, dim3(1, 1, 1), x, w, b, y, rows, d);
-    if (d == 128) return launch_ex("layernorm", layernorm_kernel<1>, grid, dim3(256), 0, s, dim3(1, 1, 1), x, w, b, y, rows, d);
-    return launch_ex("layernorm", layernorm_kernel<0>, grid, dim3(256), 0, s, dim3(1, 1, 1), x, w, b, y, rows, d);
+    if (d == 1024) return launch_ex("layernorm", layernorm_kernel<8>, grid, dim3(256), 0, s, dim3(1, 1, 1), x, w, b, y, rows, d, y_lo);
+    if (d == 128) return launch_ex("layernorm", layernorm_kernel<1>, grid, dim3(256), 0, s, dim3(1, 1, 1), x, w, b, y, rows, d, y_lo);
+    return launch_ex("layernorm", layernorm_kernel<0>, grid, dim3(256), 0, s, dim3(1, 1, 1), x, w, b, y, rows, d, y_lo);
 }
 int launch_attn_decode(const float *qkv, float *kc, float *vc, float *out, float *part, int B, int H, int max_len, int pos,
                        const int32_t *st, int n_split, cudaStream_t s, int group, int lcond, int lcond_delta) {

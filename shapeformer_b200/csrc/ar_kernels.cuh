@@ -32,13 +32,21 @@ int launch_add_target(const float *x_in, float *x_out, const int64_t *tokens, co
 int launch_take_last(const float *x, float *out, int B, int d, int T, cudaStream_t s, const int32_t *rowmap = nullptr);
 int launch_prefix_copy(float *kv, float *x0, const int32_t *dst_rows, const int32_t *src_rows, int n_dup, int H, int max_len, int T,
                        int d, int n_blocks, int64_t per_block, cudaStream_t s);
-int launch_layernorm(const float *x, const float *w, const float *b, float *y, int rows, int d, cudaStream_t s);
+int launch_layernorm(const float *x, const float *w, const float *b, float *y, int rows, int d, cudaStream_t s,
+                     float *y_lo = nullptr);
 int launch_gemv(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
                 int act, cudaStream_t s);
 int launch_linear(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
                   int act, cudaStream_t stream);
 int launch_linear_tc(const float *x, const float *W, const float *bias, const float *residual, float *y, int M, int N, int K,
                      int act, cudaStream_t stream);
+// ---- large-M GEMM (tc_big.cu): TMA-fed SS-mode 3xTF32 with the lo parts of both operands kept in memory
+constexpr int BG_MAX_UNITS = 320;     // (tile, split) units the split-K scratch is sized for
+constexpr int BG_MAX_TILES = 1024;    // arrival counters
+size_t big_partial_floats();
+int launch_split_lo(const float *x, float *lo, size_t n, cudaStream_t s);
+int launch_linear_big(const float *x, const float *x_lo, const float *W, const float *W_lo, const float *bias, const float *residual,
+                      float *y, float *y_lo, int M, int N, int K, int act, float *partial, int *tile_cnt, cudaStream_t stream);
 int64_t tc_pretiled_floats(int N, int K);
 int set_ps_timeline(unsigned long long *buf);
 int launch_tc_pretile(const float *W, float *Wt, int N, int K, cudaStream_t s);

@@ -170,4 +170,15 @@ int sfb200_ar_sample(const float *logits, int64_t *tokens, float *hist_out, cons
     return launch_sample(p, as_stream(stream));
 }
 
+int64_t sfb200_big_partial_floats(void) { return (int64_t)big_partial_floats(); }
+int sfb200_split_lo(const float *x, float *lo, int64_t n, void *stream) {
+    if (n < 0) return SFB200_E_ARG;
+    return launch_split_lo(x, lo, (size_t)n, as_stream(stream));
+}
+int sfb200_linear_big(const float *x, const float *x_lo, const float *W, const float *W_lo, const float *bias,
+                      const float *residual, float *y, float *y_lo, int M, int N, int K, int act, float *partial,
+                      int32_t *counters, void *stream) {
+    return launch_linear_big(x, x_lo, W, W_lo, bias, residual, y, y_lo, M, N, K, act, partial, counters, as_stream(stream));
+}
+
 }  // extern "C"

@@ -111,6 +111,15 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// lo part of the two-term TF32 split whose hi part is the tensor core's own truncation of v (it reads the upper 19 bits):
+// lo = rna_tf32(v - trunc_tf32(v)); the subtraction is exact.
+__device__ __forceinline__ float tf32_lo(float v) {
+    const float r = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    uint32_t o;
+    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(o) : "f"(r));
+    return __uint_as_float(o);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

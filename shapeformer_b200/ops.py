@@ -29,6 +29,31 @@ def linear_tc(x, W, bias=None, residual=None, act=None):
     return y
 
 
+def split_lo(x):
+    """Low part of the two-term TF32 split whose high part is the tensor core's truncation of x (what tc_big reads)."""
+    lib = _lib.load()
+    lo = torch.empty_like(x)
+    _lib.check(lib.sfb200_split_lo(_lib.ptr(x), _lib.ptr(lo), x.numel(), _lib.stream_ptr()), "sfb200_split_lo")
+    return lo
+
+
+def linear_big(x, W, bias=None, residual=None, act=None, want_lo=False, split_k=True):
+    """linear() through the TMA-fed large-M tensor-core kernel (csrc/tc_big.cu); lo parts of x and W made here."""
+    lib = _lib.load()
+    M, K = x.shape
+    N = W.shape[0]
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    y_lo = torch.empty_like(y) if want_lo else None
+    part = torch.empty(lib.sfb200_big_partial_floats(), dtype=torch.float32, device=x.device) if split_k else None
+    cnt = torch.zeros(1024, dtype=torch.int32, device=x.device) if split_k else None
+    _lib.check(lib.sfb200_linear_big(_lib.ptr(x), _lib.ptr(split_lo(x)), _lib.ptr(W), _lib.ptr(split_lo(W)), _lib.ptr(bias),
+                                     _lib.ptr(residual), _lib.ptr(y), _lib.ptr(y_lo), M, N, K, 1 if act == "gelu" else 0,
+                                     _lib.ptr(part), _lib.ptr(cnt), _lib.stream_ptr()), "sfb200_linear_big")
+    if split_k:
+        assert int(cnt.abs().sum()) == 0      # the arrival counters reset themselves
+    return (y, y_lo) if want_lo else y
+
+
 def linear_tc_ps(x, W, bias=None, residual=None, act=None):
     """linear() for M <= 64 rows from pre-split TF32 weight tiles (pretiles W on every call: test helper)."""
     lib = _lib.load()

@@ -80,6 +80,43 @@ def test_linear_chain_deterministic_and_repeatable(cuda):
         assert torch.equal(a, ops.linear_chain(x, W, b, residual=r))
 
 
+@pytest.mark.parametrize("M,N,K", [(65, 128, 32), (256, 1024, 1024), (512, 3072, 1024), (100, 4097, 1024), (256, 1024, 4096),
+                                   (300, 4096, 1024), (2048, 1024, 1024), (128, 256, 96 * 32)])
+@pytest.mark.parametrize("mode", ["plain", "bias_gelu", "bias_res"])
+def test_linear_big(cuda, M, N, K, mode):
+    """The TMA-fed large-M tensor-core GEMM (csrc/tc_big.cu: raw fp32 = truncated hi operand, lo parts read from memory,
+    split-K through L2 with the last arriver reducing): fp32-level accuracy against an fp64 reference, and the lo part
+    of the output it hands to a consuming GEMM."""
+    x, W, b, r = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05), rnd(N, seed=3), rnd(M, N, seed=4)
+    xd, Wd = x.double(), W.double()
+    if mode == "plain":
+        ref = xd @ Wd.t()
+        out, lo = ops.linear_big(x.to(cuda), W.to(cuda), want_lo=True)
+    elif mode == "bias_gelu":
+        ref = F.gelu(xd @ Wd.t() + b.double())
+        out, lo = ops.linear_big(x.to(cuda), W.to(cuda), b.to(cuda), act="gelu", want_lo=True)
+    else:
+        ref = r.double() + xd @ Wd.t() + b.double()
+        out, lo = ops.linear_big(x.to(cuda), W.to(cuda), b.to(cuda), residual=r.to(cuda), want_lo=True)
+    err = (out.cpu().double() - ref).abs().max().item()
+    scale = max(1.0, ref.abs().max().item())
+    assert err < 2.5e-6 * scale * max(1.0, (K / 1024) ** 0.5), (err, scale)   # single-pass TF32 would be ~1e-3
+    # lo = rna_tf32(y - trunc_tf32(y)): hi + lo reproduces y to 2^-21 relative, and lo fits TF32 (low 13 bits clear)
+    o = out.cpu()
+    hi = (o.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    assert ((hi + lo.cpu()) - o).abs().max() <= (o.abs() * 2.0 ** -20).max()
+    assert int((lo.cpu().view(torch.int32) & 0x1FFF).abs().max()) == 0
+
+
+def test_linear_big_deterministic_and_no_splitk_variant(cuda):
+    x, W, b = rnd(256, 1024, seed=1).to(cuda), rnd(1024, 1024, seed=2, scale=0.03).to(cuda), rnd(1024, seed=3).to(cuda)
+    a = ops.linear_big(x, W, b)
+    for _ in range(5):
+        assert torch.equal(a, ops.linear_big(x, W, b))          # partials are summed in split order
+    c = ops.linear_big(x, W, b, split_k=False)
+    assert (a - c).abs().max() < 1e-5
+
+
 @pytest.mark.parametrize("rows,d", [(1, 128), (64, 1024), (777, 1024)])
 def test_layernorm(cuda, rows, d):
     x, w, b = rnd(rows, d, seed=1, scale=3.0) + 0.5, rnd(d, seed=2) + 1, rnd(d, seed=3)
