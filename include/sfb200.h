@@ -191,7 +191,7 @@ int sfb200_ar_set_pretiled(sfb200_ar *h, float *pretiled, void *stream);
 int sfb200_ar_set_lo_weights(sfb200_ar *h, float *lo_blob, void *stream);
 
 /* y = act(x W^T + bias) + residual with that kernel (any M; x_lo / W_lo = low parts as produced by sfb200_split_lo; y_lo
- * optional output = low part of y; partial: sfb200_big_partial_floats() floats, counters: 1024 zeroed int32, both may be NULL
+ * optional output = low part of y; partial: sfb200_big_partial_floats() floats, counters: 2048 zeroed int32, both may be NULL
  * = no split-K).  act: 0 none, 1 exact-erf GELU. */
 int64_t sfb200_big_partial_floats(void);
 int sfb200_split_lo(const float *x, float *lo, int64_t n, void *stream);
@@ -314,6 +314,32 @@ int sfb200_attn_prefill(const float *qkv, float *kcache, float *vcache, float *o
 int sfb200_ar_sample(const float *logits, int64_t *tokens, float *hist_out, const float *noise_sample,
                      const float *noise_best, int B, int V, int max_len, int L, int L_cond, int tuple_i,
                      const int64_t *end_tokens, const sfb200_ar_sampling *sp, void *stream);
+
+/* ---- conv prologue of the decoder (csrc/conv_tc.cu): UNet3D + Upsampler of LocalDecoder (vqdif/dec.py:75-83,
+ * vqdif/unet3d.py:449-474, vqdif/updown.py:79-132) on channels-last (N, D, H, W, C) fp32 tensors ------------------------------- */
+
+/* 3x3x3 (taps = 27, padding 1) or 1x1x1 (taps = 1) convolution, no stride: out (B,Z,Y,X,Cout) = conv(in (B,Z,Y,X,Cin)) (+ bias)
+ * (ReLU when relu != 0), tcgen05 3xTF32.  in_lo = low part of the operand split of `in` (dst_lo of sfb200_conv_prep);
+ * w / w_lo = weights packed [tap][Cout][Cin] (tap = (dz*3 + dy)*3 + dx) and their low parts (sfb200_split_lo).  stats (optional):
+ * (B, Cout, 2) doubles, += per-channel sum / sum of squares of the stored output.  Cin, Cout multiples of 32 (Cout 32, 64 or a
+ * multiple of 128); Z, Y, X in {4, 8, 16, 32, 64, ...} (boxes of 128 voxels must tile the volume). */
+int sfb200_conv3d_tc(const float *in, const float *in_lo, const float *w, const float *w_lo, const float *bias, float *out,
+                     double *stats, int B, int Z, int Y, int X, int Cin, int Cout, int taps, int relu, void *stream);
+
+/* Elementwise pass between convolutions: dst (B,Z,Y,X,C0+C1) = concat(src0 (C0 channels, read at coordinate >> sh0), src1 (C1
+ * channels, >> sh1; may be NULL with C1 = 0)); with groups > 0 GroupNorm(groups, eps 1e-5, gamma, beta) from the per-channel sums
+ * st0 / st1 ((B, C, 2) doubles over n0 / n1 voxels per sample); dst_lo (optional) = low part of the operand split of dst. */
+int sfb200_conv_prep(const float *src0, int C0, int sh0, const double *st0, double n0, const float *src1, int C1, int sh1,
+                     const double *st1, double n1, const float *gamma, const float *beta, int groups, float *dst, float *dst_lo,
+                     int B, int Z, int Y, int X, void *stream);
+
+/* dst (B,Zo,Yo,Xo,C) = max-pool win^3 (win 1 or 2) of src (B,Zo*win,Yo*win,Xo*win,C); stats += per-channel sums of dst.
+ * dst may be NULL (statistics only). */
+int sfb200_pool_stats(const float *src, float *dst, double *stats, int B, int Zo, int Yo, int Xo, int C, int win, void *stream);
+
+/* Quantizer.get_code (vqdif/quantizer.py:19-30) into the channels-last layout: out (B, cells, C) = codebook[idx]; stats += sums. */
+int sfb200_gather_codes_cl(const int64_t *idx, const float *codebook, float *out, double *stats, int B, int cells, int C,
+                           int n_codes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,7 @@ from shapeformer_b200 import _lib, ops
 lib = _lib.load()
 dev = torch.device('cuda:0')
 shapes = [(1024, 1024), (3072, 1024), (4096, 1024), (1024, 4096)]
-part = torch.empty(lib.sfb200_big_partial_floats(), device=dev); cnt = torch.zeros(1024, dtype=torch.int32, device=dev)
+part = torch.empty(lib.sfb200_big_partial_floats(), device=dev); cnt = torch.zeros(2048, dtype=torch.int32, device=dev)
 for M in [int(a) for a in sys.argv[1:]] or [256, 512, 4096]:
     tot = {"big": 0.0, "tc": 0.0}
     for N, K in shapes:

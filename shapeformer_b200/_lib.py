@@ -60,6 +60,13 @@ SIGNATURES = {
     "sfb200_decoder_set_weights": (ctypes.c_int, [vp, vp]),
     "sfb200_decoder_points": (ctypes.c_int, [vp, vp, ctypes.c_int64, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int64,
                                              ctypes.c_int, ctypes.c_int, vp]),
+    "sfb200_conv3d_tc": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
+    "sfb200_conv_prep": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_double, vp, ctypes.c_int, ctypes.c_int, vp,
+                                        ctypes.c_double, vp, vp, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, vp]),
+    "sfb200_pool_stats": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
+    "sfb200_gather_codes_cl": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
     "sfb200_tokens_to_dense": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64,
                                               ctypes.c_int64, vp]),
     "sfb200_encoder_workspace_bytes": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),

@@ -125,7 +125,7 @@ static void carve(const sfb200_ar_config *c, Buffers *b) {
     b->ph_lo = take(P * d * F);
     b->pff_lo = take(P * 4 * d * F);
     b->bg_part = take((int64_t)big_partial_floats() * F);
-    b->bg_cnt = take(BG_MAX_TILES * 4);
+    b->bg_cnt = take(2 * BG_MAX_TILES * 4);
     b->total = o;
 }
 
@@ -511,7 +511,7 @@ extern "C" int sfb200_ar_begin_shared(sfb200_ar *h, int B, int L_cond, const sfb
     int32_t *st = WS_<int32_t>(h, h->buf.st);
     SFB_TRY(launch_state_init(st, L_cond, s));
     SFB_CUDA_TRY(cudaMemsetAsync(WS_<int>(h, h->buf.att_cnt), 0, (size_t)h->cfg.max_rows * h->cfg.n_head * 4, s));
-    SFB_CUDA_TRY(cudaMemsetAsync(WS_<int>(h, h->buf.bg_cnt), 0, BG_MAX_TILES * 4, s));
+    SFB_CUDA_TRY(cudaMemsetAsync(WS_<int>(h, h->buf.bg_cnt), 0, 2 * BG_MAX_TILES * 4, s));
     if (chain_active(h)) {
         SFB_TRY(chain_build_maps(h));
         SFB_CUDA_TRY(cudaMemsetAsync(WS_<unsigned int>(h, h->buf.ch_bar), 0, (CH_MAX_BARRIERS + 1) * 4, s));

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "ar_kernels.cuh"
+#include "conv_tc.cuh"
 #include "decoder_kernels.cuh"
 #include "enc_kernels.cuh"
 
@@ -179,6 +180,24 @@ int sfb200_linear_big(const float *x, const float *x_lo, const float *W, const f
                       const float *residual, float *y, float *y_lo, int M, int N, int K, int act, float *partial,
                       int32_t *counters, void *stream) {
     return launch_linear_big(x, x_lo, W, W_lo, bias, residual, y, y_lo, M, N, K, act, partial, counters, as_stream(stream));
+}
+
+int sfb200_conv3d_tc(const float *in, const float *in_lo, const float *w, const float *w_lo, const float *bias, float *out,
+                     double *stats, int B, int Z, int Y, int X, int Cin, int Cout, int taps, int relu, void *stream) {
+    return launch_conv3d_tc(in, in_lo, w, w_lo, bias, out, stats, B, Z, Y, X, Cin, Cout, taps, relu, as_stream(stream));
+}
+int sfb200_conv_prep(const float *src0, int C0, int sh0, const double *st0, double n0, const float *src1, int C1, int sh1,
+                     const double *st1, double n1, const float *gamma, const float *beta, int groups, float *dst, float *dst_lo,
+                     int B, int Z, int Y, int X, void *stream) {
+    return launch_conv_prep(src0, C0, sh0, st0, n0, src1, C1, sh1, st1, n1, gamma, beta, groups, dst, dst_lo, B, Z, Y, X,
+                            as_stream(stream));
+}
+int sfb200_pool_stats(const float *src, float *dst, double *stats, int B, int Zo, int Yo, int Xo, int C, int win, void *stream) {
+    return launch_pool_stats(src, dst, stats, B, Zo, Yo, Xo, C, win, as_stream(stream));
+}
+int sfb200_gather_codes_cl(const int64_t *idx, const float *codebook, float *out, double *stats, int B, int cells, int C,
+                           int n_codes, void *stream) {
+    return launch_gather_codes_cl(idx, codebook, out, stats, B, cells, C, n_codes, as_stream(stream));
 }
 
 }  // extern "C"

@@ -13,8 +13,9 @@
 // issues 12 tcgen05.mma.kind::tf32 (4 k-steps x 3 products, both operands from shared memory).
 // The tensor-core accumulator does not round to nearest, so accumulation chains are kept at 24 MMAs: two TMEM accumulators
 // alternate and 8 epilogue warps drain the finished one into fp32 registers (IEEE adds) while the other accumulates.
-// Split-K (small M x N grids) goes through L2: every split stores its partial tile, and the CTA that arrives last at the tile's
-// counter sums the partials in split order (deterministic) and runs the epilogue — no cluster, no second kernel.
+// Split-K (small M x N grids, at most one CTA per SM) goes through L2: every split stores its partial tile, waits for its
+// siblings at the tile's arrival counter, then sums the partials in split order (deterministic) for ITS slice of the rows and
+// runs the epilogue there — the reduction is spread over the splits; no cluster, no second kernel.
 #include <cuda.h>
 #include <string.h>
 
@@ -44,7 +45,7 @@ struct BigArgs {
     const float *bias, *residual;
     float *y, *y_lo;
     float *partial;          // split-K scratch: [tile][split][BN][128]
-    int *tile_cnt;           // one arrival counter per tile (zero between launches)
+    int *tile_cnt;           // 2 x BG_MAX_TILES counters (arrived | finished) per tile, zero between launches
     int M, N, K, act, splits;
 };
 
@@ -73,7 +74,6 @@ __global__ void __launch_bounds__(BG_THREADS, 1) tc_big_linear_kernel(const __gr
     uint64_t *dfull = empty + NS;                                       // [2]  promotion group finished in D[b]
     uint64_t *dfree = dfull + 2;                                        // [2]  D[b] drained by the 8 epilogue warps
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(dfree + 2);
-    int *s_last = reinterpret_cast<int *>(tmem_slot + 1);
 
     pdl_trigger();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -190,7 +190,9 @@ __global__ void __launch_bounds__(BG_THREADS, 1) tc_big_linear_kernel(const __gr
         tmem_dealloc<C::TM_COLS>(tmem_base);
     }
 
-    // ---- split-K: store the partial tile; the CTA that arrives last sums all partials in split order
+    // ---- split-K: every split stores its partial tile; once all splits of the tile have arrived (they are co-resident: the
+    //      grid never exceeds one CTA per SM when splits > 1) each of them reduces and finishes its own slice of the activation
+    //      rows, summing the partials in split order (deterministic)
     const int tile = blockIdx.z * gridDim.x + blockIdx.x;
     if (a.splits > 1) {
         float *part = a.partial + ((size_t)tile * a.splits + sp) * BN * 128;
@@ -201,23 +203,43 @@ __global__ void __launch_bounds__(BG_THREADS, 1) tc_big_linear_kernel(const __gr
         __threadfence();
         __syncthreads();
         if (tid == 0) {
-            const int old = atomicAdd(a.tile_cnt + tile, 1);
-            *s_last = old == a.splits - 1;
-            if (old == a.splits - 1) a.tile_cnt[tile] = 0;      // ready for the next launch
+            int *ctr = a.tile_cnt + tile;
+            asm volatile("red.release.gpu.global.add.s32 [%0], 1;\n" ::"l"(ctr) : "memory");
+            int v;
+            do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(ctr) : "memory");
+            } while (v < a.splits);
         }
         __syncthreads();
-        if (!*s_last) return;
-        __threadfence();
         if (warp >= 2) {
+            const int per = (BN + a.splits - 1) / a.splits;
+            const int c_lo = sp * per, c_hi = min(BN, c_lo + per);
             const float *p0 = a.partial + (size_t)tile * a.splits * BN * 128;
-#pragma unroll
-            for (int j = 0; j < HB; ++j) acc[j] = 0.f;
-            for (int s2 = 0; s2 < a.splits; ++s2) {
-                const float *p = p0 + (size_t)s2 * BN * 128;
-#pragma unroll
-                for (int j = 0; j < HB; ++j) acc[j] += __ldcg(p + (size_t)(half * HB + j) * 128 + row);
+            const int et = tid - 64, n = n0 + (et & 127);
+            const float bv = (a.bias && n < a.N) ? __ldg(a.bias + n) : 0.f;
+            for (int c = c_lo + (et >> 7); c < c_hi; c += 2) {
+                float r = 0.f;
+                for (int s2 = 0; s2 < a.splits; ++s2) r += __ldcg(p0 + ((size_t)s2 * BN + c) * 128 + (et & 127));
+                const int m = m0 + c;
+                if (m < a.M && n < a.N) {
+                    r += bv;
+                    if (a.act == 1) r = bg_gelu(r);
+                    const size_t off = (size_t)m * a.N + n;
+                    if (a.residual) r += __ldcg(a.residual + off);
+                    a.y[off] = r;
+                    if (a.y_lo) a.y_lo[off] = tf32_lo(r);
+                }
             }
         }
+        __syncthreads();
+        if (tid == 0) {      // the last split to finish its slice re-arms the tile's counters for the next launch
+            __threadfence();
+            if (atomicAdd(a.tile_cnt + BG_MAX_TILES + tile, 1) == a.splits - 1) {
+                a.tile_cnt[tile] = 0;
+                a.tile_cnt[BG_MAX_TILES + tile] = 0;
+            }
+        }
+        return;
     }
     // ---- epilogue: bias, activation, residual; y (and the lo part of y when a GEMM consumes it next)
     if (warp >= 2) {
@@ -298,8 +320,9 @@ static int launch_big_t(BigArgs &a, const float *x, const float *x_lo, cudaStrea
     const int n_tiles = (a.N + 127) / 128, m_tiles = (a.M + BN - 1) / BN, tiles = n_tiles * m_tiles, nch = a.K / 32;
     if (m_tiles > 65535) return SFB200_E_ARG;
     int splits = 1;
-    if (tiles < 148) {
-        splits = 148 / tiles;
+    const int sms = chain_grid_size() > 0 ? chain_grid_size() : 148;     // splits spin on their siblings: all must be co-resident
+    if (tiles < sms) {
+        splits = sms / tiles;
         if (splits > nch / 4) splits = nch / 4;
         if (splits > 16) splits = 16;
         if (splits < 1) splits = 1;
@@ -317,7 +340,7 @@ static int launch_big_t(BigArgs &a, const float *x, const float *x_lo, cudaStrea
 }
 
 // x, x_lo (M, K); W, W_lo (N, K); y (M, N); y_lo optional.  partial / tile_cnt: split-K scratch (big_partial_floats() floats,
-// BG_MAX_TILES zeroed ints) or NULL (no split-K).
+// 2 * BG_MAX_TILES zeroed ints) or NULL (no split-K).
 int launch_linear_big(const float *x, const float *x_lo, const float *W, const float *W_lo, const float *bias, const float *residual,
                       float *y, float *y_lo, int M, int N, int K, int act, float *partial, int *tile_cnt, cudaStream_t stream) {
     if (M <= 0 || N <= 0 || K <= 0 || K % 32 != 0 || !x || !x_lo || !W || !W_lo || !y) return SFB200_E_ARG;

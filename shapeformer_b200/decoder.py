@@ -103,13 +103,130 @@ def conv_prologue(sd, x, prefix="decoder.", wsplit=None, unet_mode="fp32", up_mo
     return x
 
 
+class ConvPrologueTC:
+    """UNet3D + Upsampler (vqdif/unet3d.py:449-474, updown.py:119-132) on this library's kernels (csrc/conv_tc.cu), all
+    tensors channels-last (B, D, H, W, C): tcgen05 3xTF32 implicit-GEMM convolutions fed by TMA, GroupNorm statistics
+    accumulated in the producing convolution's epilogue, GroupNorm-apply / nearest upsampling / concatenation / operand
+    split fused into one elementwise pass per layer, max-pool with its statistics.  The output IS the (B,64,64,64,32)
+    channel-last feature grid the point kernel reads — no layout transposes anywhere."""
+
+    def __init__(self, sd, device, prefix="decoder."):
+        from . import ops
+        self.lib = _lib.load()
+        self.device = device
+        self.p = {}
+
+        def conv(key, w):
+            co, ci = w.shape[:2]
+            taps = w.shape[2] * w.shape[3] * w.shape[4]
+            wp = w.reshape(co, ci, taps).permute(2, 0, 1).contiguous().reshape(taps * co, ci)     # [tap][co][ci]
+            self.p[key] = (wp, ops.split_lo(wp), ci, co, taps)
+
+        u = prefix + "unet3d."
+        self.f = sd[u + "final_conv.weight"].shape[0]
+        names = [f"{u}encoders.{i}.basic_module.SingleConv{j}." for i in range(3) for j in (1, 2)]
+        names += [f"{u}decoders.{i}.basic_module.SingleConv{j}." for i in range(2) for j in (1, 2)]
+        names += [f"{prefix}upsampler.blocks.{k}." for k in (1, 2, 4, 5)]
+        for n in names:
+            conv(n, sd[n + "conv.weight"])
+            self.p[n + "gn"] = (sd[n + "groupnorm.weight"].contiguous(), sd[n + "groupnorm.bias"].contiguous())
+        conv(u + "final", sd[u + "final_conv.weight"])
+        self.final_bias = sd[u + "final_conv.bias"].contiguous()
+        self.u, self.up = u, prefix + "upsampler."
+
+    # ---- thin wrappers -------------------------------------------------------------------------------------------------
+    def _stats(self, B, C):
+        return torch.zeros(B, C, 2, dtype=torch.float64, device=self.device)
+
+    def _conv(self, hi, lo, key, B, R, relu=True, bias=None, want_stats=True):
+        wp, wl, ci, co, taps = self.p[key]
+        out = torch.empty(B, R, R, R, co, dtype=torch.float32, device=self.device)
+        st = self._stats(B, co) if want_stats else None
+        _lib.check(self.lib.sfb200_conv3d_tc(_lib.ptr(hi), _lib.ptr(lo), _lib.ptr(wp), _lib.ptr(wl), _lib.ptr(bias), _lib.ptr(out),
+                                             _lib.ptr(st), B, R, R, R, ci, co, taps, int(relu), _lib.stream_ptr()), "sfb200_conv3d_tc")
+        return out, st
+
+    def _prep(self, B, R, src0, st0, n0, sh0=0, src1=None, st1=None, n1=1.0, sh1=0, gn=None, want_lo=True):
+        C0 = src0.shape[-1]
+        C1 = src1.shape[-1] if src1 is not None else 0
+        dst = torch.empty(B, R, R, R, C0 + C1, dtype=torch.float32, device=self.device)
+        lo = torch.empty_like(dst) if want_lo else None
+        g, b = self.p[gn] if gn else (None, None)
+        _lib.check(self.lib.sfb200_conv_prep(_lib.ptr(src0), C0, sh0, _lib.ptr(st0), float(n0), _lib.ptr(src1), C1, sh1,
+                                             _lib.ptr(st1), float(n1), _lib.ptr(g), _lib.ptr(b), 8 if gn else 0, _lib.ptr(dst),
+                                             _lib.ptr(lo), B, R, R, R, _lib.stream_ptr()), "sfb200_conv_prep")
+        return dst, lo
+
+    def _pool(self, src, B, Ro, C):
+        dst = torch.empty(B, Ro, Ro, Ro, C, dtype=torch.float32, device=self.device)
+        st = self._stats(B, C)
+        _lib.check(self.lib.sfb200_pool_stats(_lib.ptr(src), _lib.ptr(dst), _lib.ptr(st), B, Ro, Ro, Ro, C, 2, _lib.stream_ptr()),
+                   "sfb200_pool_stats")
+        return dst, st
+
+    def double_conv(self, pre, B, R, src0, st0, n0, sh0=0, src1=None, st1=None, n1=1.0, sh1=0):
+        """DoubleConv 'gcr' x2 (unet3d.py:103-144): GroupNorm -> conv -> ReLU, twice."""
+        hi, lo = self._prep(B, R, src0, st0, n0, sh0, src1, st1, n1, sh1, gn=pre + "SingleConv1.gn")
+        t, st = self._conv(hi, lo, pre + "SingleConv1.", B, R)
+        hi, lo = self._prep(B, R, t, st, R ** 3, gn=pre + "SingleConv2.gn")
+        return self._conv(hi, lo, pre + "SingleConv2.", B, R)
+
+    def from_codes(self, code_ind, codebook):
+        """(B, r, r, r) int64 code grid -> (B, 4r, 4r, 4r, 32) feature grid (r = 16); Quantizer.get_code fused into the gather."""
+        B, r = code_ind.shape[0], code_ind.shape[1]
+        n_codes, C = codebook.shape
+        x = torch.empty(B, r, r, r, C, dtype=torch.float32, device=self.device)
+        st = self._stats(B, C)
+        _lib.check(self.lib.sfb200_gather_codes_cl(_lib.ptr(code_ind), _lib.ptr(codebook), _lib.ptr(x), _lib.ptr(st), B, r ** 3, C,
+                                                   n_codes, _lib.stream_ptr()), "sfb200_gather_codes_cl")
+        return self.from_features(x, st)
+
+    def from_nchw(self, quant_feat):
+        """(B, C, r, r, r) quantised features (VQDIF.decode's input) -> feature grid."""
+        B, C, r = quant_feat.shape[:3]
+        x = quant_feat.permute(0, 2, 3, 4, 1).contiguous()
+        st = self._stats(B, C)
+        _lib.check(self.lib.sfb200_pool_stats(_lib.ptr(x), None, _lib.ptr(st), B, r, r, r, C, 1, _lib.stream_ptr()), "sfb200_pool_stats")
+        return self.from_features(x, st)
+
+    def from_features(self, x, st):
+        """x (B, r, r, r, C) channels-last quantised features + their per-channel sums -> (B, 4r, 4r, 4r, 32)."""
+        B, r = x.shape[0], x.shape[1]
+        u = self.u
+        # ---- UNet3D encoders (max-pool 2 before levels 1, 2)
+        e0, s0 = self.double_conv(f"{u}encoders.0.basic_module.", B, r, x, st, r ** 3)
+        p, sp = self._pool(e0, B, r // 2, e0.shape[-1])
+        e1, s1 = self.double_conv(f"{u}encoders.1.basic_module.", B, r // 2, p, sp, (r // 2) ** 3)
+        p, sp = self._pool(e1, B, r // 4, e1.shape[-1])
+        e2, s2 = self.double_conv(f"{u}encoders.2.basic_module.", B, r // 4, p, sp, (r // 4) ** 3)
+        # ---- decoders: nearest x2 of the deeper features, concat [skip, up] (unet3d.py:365-371), DoubleConv
+        d0, t0 = self.double_conv(f"{u}decoders.0.basic_module.", B, r // 2, e1, s1, (r // 2) ** 3, 0, e2, s2, (r // 4) ** 3, 1)
+        d1, t1 = self.double_conv(f"{u}decoders.1.basic_module.", B, r, e0, s0, r ** 3, 0, d0, t0, (r // 2) ** 3, 1)
+        hi, lo = self._prep(B, r, d1, None, 1.0)
+        f, _ = self._conv(hi, lo, u + "final", B, r, relu=False, bias=self.final_bias, want_stats=False)
+        # ---- Upsampler: 2 x [nearest x2, 'crg', 'crg'] = conv -> ReLU -> GroupNorm (updown.py:79-132); the GroupNorm of a layer
+        #      is applied by the next layer's prep pass (or by the final pass that writes the feature grid)
+        R = 2 * r
+        hi, lo = self._prep(B, R, f, None, 1.0, sh0=1)
+        a, sa = self._conv(hi, lo, self.up + "blocks.1.", B, R)
+        hi, lo = self._prep(B, R, a, sa, R ** 3, gn=self.up + "blocks.1.gn")
+        a, sa = self._conv(hi, lo, self.up + "blocks.2.", B, R)
+        hi, lo = self._prep(B, 2 * R, a, sa, R ** 3, sh0=1, gn=self.up + "blocks.2.gn")
+        R *= 2
+        a, sa = self._conv(hi, lo, self.up + "blocks.4.", B, R)
+        hi, lo = self._prep(B, R, a, sa, R ** 3, gn=self.up + "blocks.4.gn")
+        a, sa = self._conv(hi, lo, self.up + "blocks.5.", B, R)
+        grid, _ = self._prep(B, R, a, sa, R ** 3, gn=self.up + "blocks.5.gn", want_lo=False)
+        return grid
+
+
 class ImplicitDecoder:
     """decode_index for batches of code grids.  `sd`: VQDIF state dict (decoder.*, quantizer.embedding.weight).
     impl: 0 = tcgen05 tensor-core point kernel (default), 1 = fp32 FFMA point kernel (kept for cross-checking)."""
     _active = {}     # device index -> instance whose MLP weights currently sit in that device's constant bank
 
     def __init__(self, sd, device, impl=0, prefix="decoder.", codebook_key="quantizer.embedding.weight", unet_mode="fp32",
-                 up_mode="3xtf32"):
+                 up_mode="3xtf32", prologue=None):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -120,6 +237,12 @@ class ImplicitDecoder:
         self.codebook = self.sd[codebook_key]
         self.mlp = pack_mlp_weights(self.sd, prefix).to(self.device).contiguous()
         self.unet_mode, self.up_mode = unet_mode, up_mode
+        # conv prologue: "tc" = this library's tcgen05 kernels (csrc/conv_tc.cu, default); "cudnn" = the reference's op set
+        # through PyTorch / cuDNN (kept as a cross-check; SFB200_PROLOGUE=cudnn selects it globally)
+        import os
+        self.prologue = prologue or os.environ.get("SFB200_PROLOGUE", "tc")
+        with torch.cuda.device(self.device):
+            self.conv_tc = ConvPrologueTC(self.sd, self.device, prefix) if self.prologue == "tc" else None
         self.wsplit = {}
         for k, v in self.sd.items():
             three = ("upsampler." in k and up_mode != "fp32") or ("unet3d." in k and unet_mode != "fp32")
@@ -148,6 +271,8 @@ class ImplicitDecoder:
     @_on_device
     def feature_grid(self, quant_feat):
         """(B,128,16,16,16) quantised features -> channel-last (B,64,64,64,32) decoder feature grid."""
+        if self.conv_tc is not None:
+            return self.conv_tc.from_nchw(quant_feat.to(self.device, torch.float32))
         g = conv_prologue(self.sd, quant_feat, self.prefix, self.wsplit, self.unet_mode, self.up_mode).contiguous()
         B, C = g.shape[:2]
         S = g.shape[2] * g.shape[3] * g.shape[4]
@@ -155,6 +280,13 @@ class ImplicitDecoder:
         _lib.check(self.lib.sfb200_grid_to_channels_last(_lib.ptr(g), _lib.ptr(out), B, C, S, _lib.stream_ptr()),
                    "grid_to_channels_last")
         return out
+
+    @_on_device
+    def feature_grid_from_codes(self, code_ind):
+        """(B,16,16,16) int64 codes -> (B,64,64,64,32) feature grid (Quantizer.get_code + conv prologue)."""
+        if self.conv_tc is not None:
+            return self.conv_tc.from_codes(code_ind.to(self.device).long().contiguous(), self.codebook)
+        return self.feature_grid(self.get_code(code_ind))
 
     @_on_device
     def decode_points(self, grid_cl, Xtg, impl=None, sigmoid=False):
@@ -177,18 +309,34 @@ class ImplicitDecoder:
                    "decoder_points")
         return out
 
+    # shapes per pass of the conv prologue + point kernel: the 64^3 x 32 feature grids (33.5 MB per shape) and the conv
+    # intermediates of a pass stay a few GB however large the batch is
+    SHAPES_PER_PASS = 32
+
+    def _chunked(self, first, Xtg, impl, sigmoid, prologue):
+        B = first.shape[0]
+        if B <= self.SHAPES_PER_PASS:
+            return self.decode_points(prologue(first), Xtg, impl, sigmoid)
+        outs = []
+        for b0 in range(0, B, self.SHAPES_PER_PASS):
+            b1 = min(B, b0 + self.SHAPES_PER_PASS)
+            x = Xtg if Xtg.shape[0] == 1 else Xtg[b0:b1]
+            outs.append(self.decode_points(prologue(first[b0:b1]), x, impl, sigmoid))
+        return torch.cat(outs, 0)
+
     def decode(self, quant_feat, Xtg, impl=None):
-        """VQDIF.decode (vqdif/vqdif.py:60-72); the 256^3 chunking is unnecessary (N is an int64 in the kernel)."""
-        return {"logits": self.decode_points(self.feature_grid(quant_feat), Xtg, impl)[..., None]}
+        """VQDIF.decode (vqdif/vqdif.py:60-72); the 256^3 chunking is unnecessary (N is an int64 in the kernel); large batches
+        go through the prologue SHAPES_PER_PASS shapes at a time."""
+        return {"logits": self._chunked(quant_feat, Xtg, impl, False, self.feature_grid)[..., None]}
 
     def decode_index(self, code_ind, Xtg, impl=None):
         """VQDIF.decode_index (vqdif/vqdif.py:74-76)."""
-        return self.decode(self.get_code(code_ind), Xtg, impl)
+        return {"logits": self._chunked(code_ind, Xtg, impl, False, self.feature_grid_from_codes)[..., None]}
 
     def occupancy(self, code_ind, Xtg, impl=None):
         """decode_index followed by the sigmoid of decode_sample_indices (shapeformer/shapeformer.py:382-391), batched:
         (B,R,R,R) int64 codes -> (B, N) occupancy in [0,1]."""
-        return self.decode_points(self.feature_grid(self.get_code(code_ind)), Xtg, impl, sigmoid=True)
+        return self._chunked(code_ind, Xtg, impl, True, self.feature_grid_from_codes)
 
     @_on_device
     def tokens_to_dense(self, tokens, empty_index, res=16, end_tokens=(4096, 4096)):

@@ -45,8 +45,9 @@ def linear_big(x, W, bias=None, residual=None, act=None, want_lo=False, split_k=
     y = torch.empty(M, N, dtype=torch.float32, device=x.device)
     y_lo = torch.empty_like(y) if want_lo else None
     part = torch.empty(lib.sfb200_big_partial_floats(), dtype=torch.float32, device=x.device) if split_k else None
-    cnt = torch.zeros(1024, dtype=torch.int32, device=x.device) if split_k else None
-    _lib.check(lib.sfb200_linear_big(_lib.ptr(x), _lib.ptr(split_lo(x)), _lib.ptr(W), _lib.ptr(split_lo(W)), _lib.ptr(bias),
+    cnt = torch.zeros(2048, dtype=torch.int32, device=x.device) if split_k else None
+    x_lo, W_lo = split_lo(x), split_lo(W)      # keep the temporaries alive across the launch
+    _lib.check(lib.sfb200_linear_big(_lib.ptr(x), _lib.ptr(x_lo), _lib.ptr(W), _lib.ptr(W_lo), _lib.ptr(bias),
                                      _lib.ptr(residual), _lib.ptr(y), _lib.ptr(y_lo), M, N, K, 1 if act == "gelu" else 0,
                                      _lib.ptr(part), _lib.ptr(cnt), _lib.stream_ptr()), "sfb200_linear_big")
     if split_k:

@@ -70,6 +70,20 @@ def test_bench_batch_shipped_model_long_run(cuda):
     assert worst < 2e-4, worst
 
 
+def test_large_batch_decode_path(cuda):
+    """Decode batches of more than 64 rows (the default bench batch is 512) leave the persistent chain kernel for the TMA-fed
+    large-M GEMM (csrc/tc_big.cu) + LayerNorm / split kernels: 160 rows = 40 shapes x sample_n 4 of the shipped model, tokens
+    bit-exact against the KV-cached oracle."""
+    cfg = synth.SHIPPED_GPT
+    sd = synth.gpt_state_dict(cfg, seed=314, peaky=True)
+    B, n, Lc, steps = 160, 4, 64, 40
+    c = synth.cond_indices(B // n, Lc, seed=2000).repeat_interleave(n, 0)
+    noise = util.noise_from_seed(19, steps, B, 4097)
+    worst = run_pair(cuda, cfg, sd, c, steps, 50, 0.0, True, noise)
+    print(f"large-batch decode path: tokens bit-exact over {steps} steps x {B} rows; max |dlogit| = {worst:.2e}")
+    assert worst < 2e-4, worst
+
+
 def test_cfg2_single_row_greedy_512(cuda):
     """BASELINE cfg 2: B = 1, L_cond 256, 512 greedy steps (top_k 1, top_p 0.001), fixed-length mode."""
     cfg = synth.SHIPPED_GPT

@@ -209,14 +209,39 @@ def test_shared_conditioning_prefill_equals_per_row_prefill(cuda, pattern):
     assert torch.equal(outs[1][0][:, :ox.shape[1]], ox)
 
 
+def test_conv_prologue_tc_kernels(cuda):
+    """The shipped conv prologue (csrc/conv_tc.cu: tcgen05 3xTF32 implicit-GEMM convs, fused GroupNorm / upsample / concat passes)
+    through decode_index: occupancy within the north-star 1e-4 of the oracle, and close to the cuDNN fp32 path."""
+    sd = synth.vqdif_state_dict(seed=4)
+    code = synth.code_grids(3, seed=3)
+    Xtg = torch.rand(1, 20000, 3, generator=torch.Generator().manual_seed(0)) * 2 - 1
+    ref = O.decode_index(sd, code, Xtg.expand(3, -1, -1))["logits"][..., 0]
+    dec = decoder.ImplicitDecoder(sd, cuda, prologue="tc")
+    assert dec.conv_tc is not None
+    out = dec.decode_index(code, Xtg)["logits"][..., 0].cpu()
+    err = (out - ref).abs().max().item()
+    occ_err = (torch.sigmoid(out) - torch.sigmoid(ref)).abs().max().item()
+    grid = dec.feature_grid_from_codes(code).cpu()
+    ref_grid = decoder.ImplicitDecoder(sd, cuda, prologue="cudnn", unet_mode="fp32", up_mode="fp32").feature_grid_from_codes(code).cpu()
+    gerr = (grid - ref_grid).abs().max().item()
+    print(f"tc conv prologue: max |dlogit| = {err:.2e}, max |docc| = {occ_err:.2e}, feature grid vs cuDNN fp32 {gerr:.2e} "
+          f"(max |grid| {ref_grid.abs().max().item():.2f})")
+    assert occ_err < 1e-4 and err < 2e-4, (occ_err, err)
+    assert gerr < 2e-4 * max(1.0, ref_grid.abs().max().item()), gerr
+    # decode (NCDHW features in) takes the same path
+    out2 = dec.decode(dec.get_code(code), Xtg)["logits"][..., 0].cpu()
+    assert (out2 - out).abs().max() < 1e-6
+
+
 @pytest.mark.parametrize("unet_mode,up_mode", [("fp32", "fp32"), ("fp32", "3xtf32"), ("3xtf32", "3xtf32")])
 def test_conv_prologue_precision_modes(cuda, unet_mode, up_mode):
-    """The 3xTF32 tensor-core convolutions keep the decoded logits within the 1e-4 budget (plain TF32 does not)."""
+    """The cuDNN cross-check path: 3xTF32 tensor-core convolutions keep the decoded logits within the 1e-4 budget (plain TF32
+    does not)."""
     sd = synth.vqdif_state_dict(seed=4)
     code = synth.code_grids(2, seed=3)
     Xtg = torch.rand(1, 20000, 3, generator=torch.Generator().manual_seed(0)) * 2 - 1
     ref = O.decode_index(sd, code, Xtg.expand(2, -1, -1))["logits"][..., 0]
-    dec = decoder.ImplicitDecoder(sd, cuda, unet_mode=unet_mode, up_mode=up_mode)
+    dec = decoder.ImplicitDecoder(sd, cuda, unet_mode=unet_mode, up_mode=up_mode, prologue="cudnn")
     out = dec.decode_index(code, Xtg)["logits"][..., 0].cpu()
     err = (out - ref).abs().max().item()
     occ_err = (torch.sigmoid(out) - torch.sigmoid(ref)).abs().max().item()

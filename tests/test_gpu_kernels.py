@@ -290,3 +290,78 @@ def test_linear_tc_presplit(cuda, M, N, K, mode):
     err = (out.cpu().double() - ref).abs().max().item()
     scale = max(1.0, ref.abs().max().item())
     assert err < 2.5e-6 * scale * max(1.0, (K / 1024) ** 0.5), (err, scale)
+
+
+# ---- conv prologue kernels (csrc/conv_tc.cu) ---------------------------------------------------------------------------
+def _conv_tc(cuda, x_cl, w, bias=None, relu=False):
+    """x_cl (B,R,R,R,Cin) CPU, w (Cout,Cin,k,k,k) CPU -> (out (B,R,R,R,Cout), stats (B,Cout,2)) through sfb200_conv3d_tc."""
+    from shapeformer_b200 import _lib
+    lib = _lib.load()
+    B, R, Cin = x_cl.shape[0], x_cl.shape[1], x_cl.shape[-1]
+    Cout, taps = w.shape[0], w.shape[2] ** 3
+    hi = x_cl.to(cuda).contiguous()
+    lo = ops.split_lo(hi)
+    wp = w.reshape(Cout, Cin, taps).permute(2, 0, 1).contiguous().reshape(taps * Cout, Cin).to(cuda)
+    wl = ops.split_lo(wp)
+    out = torch.empty(B, R, R, R, Cout, device=cuda)
+    st = torch.zeros(B, Cout, 2, dtype=torch.float64, device=cuda)
+    bb = bias.to(cuda) if bias is not None else None
+    _lib.check(lib.sfb200_conv3d_tc(_lib.ptr(hi), _lib.ptr(lo), _lib.ptr(wp), _lib.ptr(wl), _lib.ptr(bb), _lib.ptr(out), _lib.ptr(st),
+                                    B, R, R, R, Cin, Cout, taps, int(relu), _lib.stream_ptr()), "conv3d_tc")
+    return out.cpu(), st.cpu()
+
+
+@pytest.mark.parametrize("B,R,Cin,Cout,k", [(2, 16, 128, 128, 3), (3, 8, 128, 256, 3), (3, 4, 256, 512, 3), (2, 8, 768, 256, 3),
+                                            (1, 32, 64, 64, 3), (1, 64, 32, 32, 3), (2, 16, 128, 128, 1), (1, 32, 128, 64, 3)])
+def test_conv3d_tc(cuda, B, R, Cin, Cout, k):
+    """tcgen05 implicit-GEMM conv3d (TMA boxes with zero-filled halo = the padding; 3xTF32) against torch fp64 conv3d, incl.
+    the per-channel sums of the epilogue (the next GroupNorm's statistics), boxes spanning two samples (4^3) and odd B."""
+    x = rnd(B, R, R, R, Cin, seed=1)
+    w = rnd(Cout, Cin, k, k, k, seed=2, scale=1.0 / math.sqrt(Cin * k ** 3))
+    bias = rnd(Cout, seed=3) if k == 1 else None
+    relu = k == 3
+    out, st = _conv_tc(cuda, x, w, bias, relu)
+    ref = F.conv3d(x.permute(0, 4, 1, 2, 3).double(), w.double(), bias.double() if bias is not None else None, padding=k // 2)
+    if relu:
+        ref = F.relu(ref)
+    ref = ref.permute(0, 2, 3, 4, 1)
+    err = (out.double() - ref).abs().max().item()
+    assert err < 4e-6 * max(1.0, ref.abs().max().item()), err        # single-pass TF32 would be ~1e-3
+    s_ref = torch.stack([ref.sum((1, 2, 3)), (ref * ref).sum((1, 2, 3))], -1)
+    assert (st - s_ref).abs().max() < 1e-3 * max(1.0, s_ref.abs().max().item())
+
+
+def test_conv_prep_groupnorm_upsample_concat_and_pool(cuda):
+    """conv_prep: GroupNorm(8) from per-channel sums over the CONCATENATION of a skip tensor and a x2-upsampled tensor, operand
+    split on store; pool_stats: max-pool 2 + sums — against torch."""
+    from shapeformer_b200 import _lib
+    lib = _lib.load()
+    B, R, C0, C1 = 2, 8, 64, 128
+    a, b = rnd(B, R, R, R, C0, seed=1, scale=2.0) + 0.3, rnd(B, R // 2, R // 2, R // 2, C1, seed=2) - 0.5
+    gamma, beta = rnd(C0 + C1, seed=3) + 1, rnd(C0 + C1, seed=4)
+    def sums(t):
+        st = torch.zeros(B, t.shape[-1], 2, dtype=torch.float64, device=cuda)
+        _lib.check(lib.sfb200_pool_stats(_lib.ptr(t), None, _lib.ptr(st), B, t.shape[1], t.shape[1], t.shape[1], t.shape[-1], 1,
+                                         _lib.stream_ptr()), "pool_stats")
+        return st
+    ad, bd = a.to(cuda), b.to(cuda)
+    sa, sb = sums(ad), sums(bd)
+    dst, lo = torch.empty(B, R, R, R, C0 + C1, device=cuda), torch.empty(B, R, R, R, C0 + C1, device=cuda)
+    gd, btd = gamma.to(cuda), beta.to(cuda)       # keep the device copies alive across the launch
+    _lib.check(lib.sfb200_conv_prep(_lib.ptr(ad), C0, 0, _lib.ptr(sa), float(R ** 3), _lib.ptr(bd), C1, 1, _lib.ptr(sb),
+                                    float((R // 2) ** 3), _lib.ptr(gd), _lib.ptr(btd), 8, _lib.ptr(dst),
+                                    _lib.ptr(lo), B, R, R, R, _lib.stream_ptr()), "conv_prep")
+    cat = torch.cat([a.permute(0, 4, 1, 2, 3), F.interpolate(b.permute(0, 4, 1, 2, 3), scale_factor=2, mode="nearest")], 1)
+    ref = F.group_norm(cat, 8, gamma, beta, 1e-5).permute(0, 2, 3, 4, 1)
+    assert (dst.cpu() - ref).abs().max() < 2e-5
+    d = dst.cpu()
+    hi = (d.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    assert ((hi + lo.cpu()) - d).abs().max() <= (d.abs() * 2.0 ** -20).max()
+    # max-pool 2 + sums
+    pooled = torch.empty(B, R // 2, R // 2, R // 2, C0, device=cuda)
+    st = torch.zeros(B, C0, 2, dtype=torch.float64, device=cuda)
+    _lib.check(lib.sfb200_pool_stats(_lib.ptr(ad), _lib.ptr(pooled), _lib.ptr(st), B, R // 2, R // 2, R // 2, C0, 2, _lib.stream_ptr()),
+               "pool_stats")
+    pref = F.max_pool3d(a.permute(0, 4, 1, 2, 3), 2).permute(0, 2, 3, 4, 1)
+    assert torch.equal(pooled.cpu(), pref.contiguous())
+    assert (st.cpu()[..., 0] - pref.double().sum((1, 2, 3))).abs().max() < 1e-6
