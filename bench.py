@@ -446,6 +446,10 @@ def main():
     # ---- e2e: through the reference-facing model API with HOST buffers (pinned), copies inside the timed region
     e2e = None
     if not args.no_e2e:
+        # the e2e arm keeps the reference's logits history: its sampler replaces the value arm's (one KV cache alive at a time)
+        del sampler
+        model.transformer._samplers.clear()
+        torch.cuda.empty_cache()
         model.history_device = "cpu"
         tok_host = torch.empty(B, S, 2, dtype=torch.int64).pin_memory()
         occ_host = torch.empty(B, R ** 3, dtype=torch.float32).pin_memory()
@@ -468,8 +472,9 @@ def main():
         e2e = {"value": rows_total * n_e2e / (ms_e * 1e-3), "unit": "shapes/s", "steps": n_e2e,
                "h2d_bytes_per_step": int(c_host.numel() * 8 + xtg_host.numel() * 4),
                "d2h_bytes_per_step": int(tok_host.numel() * 8 + occ_host.numel() * 4 + hist_bytes),
-               "api": "ShapeFormer.sample(...) [fresh token tensor + the reference's CPU logits history, fresh tensors] -> "
-                      "tokens_to_dense -> VQDIF occupancy; pinned host buffers for inputs/outputs"}
+               "api": "ShapeFormer.sample(...) [fresh token tensor + the reference's CPU logits history in fresh tensors, streamed "
+                      "to the host chunk by chunk while the next chunk is computed] -> tokens_to_dense -> VQDIF occupancy; pinned "
+                      "host buffers for inputs/outputs"}
         model.history_device = None
 
     cpu = None

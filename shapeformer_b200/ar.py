@@ -159,6 +159,14 @@ class ARSampler:
         torch.cuda.current_stream().synchronize()
         return int(self.status_host[0]), int(self.status_host[1])
 
+    def history_views(self, B):
+        """Device views (B, max_steps, V) of the two logits-history slabs (rows beyond the steps run so far are stale)."""
+        V = self.spec["vocab_sizes"]
+        n0 = self.max_rows * self.max_steps * V[0]
+        h0 = self.hist[:n0].view(self.max_rows, self.max_steps, V[0])[:B]
+        h1 = self.hist[n0:n0 + self.max_rows * self.max_steps * V[1]].view(self.max_rows, self.max_steps, V[1])[:B]
+        return [h0, h1]
+
     def _noise_buf(self, B):
         buf = self._noise.get(B)
         if buf is None:
@@ -186,10 +194,12 @@ class ARSampler:
 
     def _sample(self, c_indices, max_steps, top_k=100, top_p=0.8, temperature=1.0, best_in_first=False,
                mask_invalid=True, mask_invalid_completion=False, noise=None, generator=None, use_graph=True,
-               stop_early=True, share_prefix=True):
+               stop_early=True, share_prefix=True, on_chunk=None):
         """Run the AR loop.  c_indices (B, L_c, 2) int64 (any device).  noise: optional (>= max_steps, 4, B, Vmax)
         tensor of Exp(1) draws to use instead of the device RNG (parity tests).  Returns (x (B, steps, 2) int64 on the
-        device, [hist0, hist1] device views (B, steps, V) or None)."""
+        device, [hist0, hist1] device views (B, steps, V) or None).  on_chunk(first_step, n_steps): called right after a chunk of
+        steps has been enqueued (before the host waits for it) — the hook through which ShapeFormer.sample streams the logits
+        history to the host while the next chunk runs."""
         B, L_c, tn = c_indices.shape
         if tn != 2:
             raise _lib.Sfb200Error("tuple_n must be 2 (pos, val)")
@@ -228,6 +238,8 @@ class ARSampler:
                 self._draw_noise(slab, n, B, generator)
             _lib.check(self.lib.sfb200_ar_steps(self.handle, n, _lib.ptr(slab), int(bool(use_graph)), stream),
                        "sfb200_ar_steps")
+            if on_chunk is not None:
+                on_chunk(done, n)
             done += n
             if stop_early:
                 _, ended = self._read_status()

@@ -12,6 +12,62 @@ import torch.nn as nn
 from ...xgutils import sysutil
 
 
+class _HistoryStreamer:
+    """The reference returns the masked logits of every step on the CPU (shapeformer.py:94,118): 16.8 MB per row, 8.6 GB for a
+    512-row batch.  Instead of one big device->host copy + host copy after the loop, every chunk of steps travels while the NEXT
+    chunk is being computed: a side stream copies the chunk's slab into a pinned staging ring as soon as the chunk has finished
+    on the GPU, and the host thread — idle while the GPU works — moves the previous chunk from the ring into the fresh result
+    tensors.  Only the last chunk's transfer is exposed."""
+    _ring = {}          # (B, chunk, V tuple) -> [pinned (2 slots) per tuple element], reused across calls (never returned)
+    _side = {}          # device index -> copy stream
+
+    def __init__(self, sampler, B):
+        self.s, self.B = sampler, B
+        self.V = list(sampler.spec["vocab_sizes"])
+        self.dev = sampler.device
+        self.views = sampler.history_views(B)
+        self.out = [torch.empty(B, sampler.max_steps, v, dtype=torch.float32) for v in self.V]     # fresh, pageable
+        key = (B, sampler.chunk_steps, tuple(self.V))
+        ring = _HistoryStreamer._ring.get(key)
+        if ring is None:
+            _HistoryStreamer._ring.clear()
+            ring = [[torch.empty(B, sampler.chunk_steps, v, dtype=torch.float32).pin_memory() for _ in range(2)] for v in self.V]
+            _HistoryStreamer._ring[key] = ring
+        self.ring = ring
+        idx = self.dev.index if self.dev.index is not None else torch.cuda.current_device()
+        if idx not in _HistoryStreamer._side:
+            _HistoryStreamer._side[idx] = torch.cuda.Stream(device=self.dev)
+        self.side = _HistoryStreamer._side[idx]
+        self.pending = []     # (first_step, n, slot, event)
+        self.k = 0
+
+    def _drain(self, upto):
+        while len(self.pending) > upto:
+            first, n, slot, ev = self.pending.pop(0)
+            ev.synchronize()
+            for i in range(len(self.V)):
+                self.out[i][:, first:first + n].copy_(self.ring[i][slot][:, :n])
+
+    def on_chunk(self, first, n):
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream())          # fires when this chunk's steps have run
+        self._drain(1)                                     # the slot about to be reused must have been moved out
+        slot = self.k % 2
+        self.k += 1
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(done)
+            for i in range(len(self.V)):
+                self.ring[i][slot][:, :n].copy_(self.views[i][:, first:first + n], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.pending.append((first, n, slot, ev))
+        self._drain(1)                                     # move the PREVIOUS chunk while the GPU runs this one
+
+    def finish(self, steps):
+        self._drain(0)
+        return [o[:, :steps] for o in self.out]
+
+
 class ShapeFormer(nn.Module):
     def __init__(self, tuple_n=None, block_size=None, end_tokens=None, vocab_sizes=None, extra_vocab_sizes=None,
                  voxel_res=16, transformer_opt=None, representer_opt=None, optim_opt=None):
@@ -47,26 +103,30 @@ class ShapeFormer(nn.Module):
         rep = self.representer
         keep = self.history_device is not None
         s = self.transformer.sampler(B, L_c, max_steps, self.end_tokens, keep_history=keep)
+        stream_hist = keep and self.history_device == "cpu" and not self.zero_copy_outputs
         with torch.cuda.device(self.device):
+            streamer = _HistoryStreamer(s, B) if stream_hist else None
             x, hist = self._run_sampler(s, c_indices, max_steps, top_k, top_p, temperature, best_in_first, rep, noise,
-                                        generator)
+                                        generator, streamer.on_chunk if streamer else None)
+            if streamer:
+                hist = streamer.finish(x.shape[1])
         if hist is None:
             hist = [None] * tuple_n
+        elif streamer:
+            pass
         elif self.history_device == "cpu":
             with torch.cuda.device(self.device):
                 hist = [self._to_host(h, i) for i, h in enumerate(hist)]
-            if not self.zero_copy_outputs:
-                hist = [h.clone() for h in hist]
         elif not self.zero_copy_outputs:
             hist = [h.clone() for h in hist]
         return (x if self.zero_copy_outputs else x.clone()), hist
 
     @staticmethod
-    def _run_sampler(s, c_indices, max_steps, top_k, top_p, temperature, best_in_first, rep, noise, generator):
+    def _run_sampler(s, c_indices, max_steps, top_k, top_p, temperature, best_in_first, rep, noise, generator, on_chunk=None):
         return s.sample(c_indices, max_steps, top_k=top_k, top_p=top_p, temperature=temperature,
                            best_in_first=best_in_first, mask_invalid=getattr(rep, "mask_invalid", True),
                            mask_invalid_completion=getattr(rep, "mask_invalid_completion", False), noise=noise,
-                           generator=generator)
+                           generator=generator, on_chunk=on_chunk)
 
     _pinned = {}
 
