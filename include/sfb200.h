@@ -318,7 +318,10 @@ int sfb200_ar_sample(const float *logits, int64_t *tokens, float *hist_out, cons
 /* ---- conv prologue of the decoder (csrc/conv_tc.cu): UNet3D + Upsampler of LocalDecoder (vqdif/dec.py:75-83,
  * vqdif/unet3d.py:449-474, vqdif/updown.py:79-132) on channels-last (N, D, H, W, C) fp32 tensors ------------------------------- */
 
-/* 3x3x3 (taps = 27, padding 1) or 1x1x1 (taps = 1) convolution, no stride: out (B,Z,Y,X,Cout) = conv(in (B,Z,Y,X,Cin)) (+ bias)
+/* taps = 8: the 3x3x3 convolution that FOLLOWS a nearest-neighbour x2 upsampling (updown.py:119-132) in sub-pixel form: `in` is the
+ * low-resolution tensor (B,Z,Y,X,Cin), out is (B,2Z,2Y,2X,Cout); w packed [phase (pz,py,px)][tap (tz,ty,tz)][Cout][Cin] with the
+ * original taps that read the same input voxel summed (decoder.py::pack_subpixel_weights).
+ * 3x3x3 (taps = 27, padding 1) or 1x1x1 (taps = 1) convolution, no stride: out (B,Z,Y,X,Cout) = conv(in (B,Z,Y,X,Cin)) (+ bias)
  * (ReLU when relu != 0), tcgen05 3xTF32.  in_lo = low part of the operand split of `in` (dst_lo of sfb200_conv_prep);
  * w / w_lo = weights packed [tap][Cout][Cin] (tap = (dz*3 + dy)*3 + dx) and their low parts (sfb200_split_lo).  stats (optional):
  * (B, Cout, 2) doubles, += per-channel sum / sum of squares of the stored output.  Cin, Cout multiples of 32 (Cout 32, 64 or a

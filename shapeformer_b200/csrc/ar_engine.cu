@@ -340,7 +340,7 @@ static int block_prefill(sfb200_ar *h, int g, int l, float *x, int row0, int row
 
 // Decode attention of block (g, l) for the newest position (read from the device state), bracketed by events when the
 // bench's attention profiling is on.
-static int attn_step(sfb200_ar *h, int g, int l, cudaStream_t s) {
+static int attn_step(sfb200_ar *h, int g, int l, cudaStream_t s, float *att_lo = nullptr) {
     const int d = h->cfg.n_embd, H = h->cfg.n_head, B = h->B;
     const int32_t *st = WS_<int32_t>(h, h->buf.st);
     float *qkv = WS_<float>(h, h->buf.qkv), *att = WS_<float>(h, h->buf.att), *part = WS_<float>(h, h->buf.part);
@@ -354,12 +354,16 @@ static int attn_step(sfb200_ar *h, int g, int l, cudaStream_t s) {
         }
         SFB_CUDA_TRY(cudaEventRecord((*h->ev)[h->ev_used], s));
     }
-    if (h->attn_group > 1 && h->use_grouped_attn)
+    // att_lo: low part of the attention output for a tc_big projection — written by the grouped kernel's combine, by a
+    // split_lo pass after the per-row kernel
+    if (h->attn_group > 1 && h->use_grouped_attn) {
         SFB_TRY(launch_attn_grouped(qkv, kcache(h, g, l, 0), vcache(h, g, l, 0), att, part, WS_<int>(h, h->buf.att_cnt), B, H,
-                                    h->cfg.max_len, 0, st, h->attn_group, 0, g == 1 ? -1 : 0, s));
-    else
+                                    h->cfg.max_len, 0, st, h->attn_group, 0, g == 1 ? -1 : 0, s, att_lo));
+    } else {
         SFB_TRY(launch_attn_decode(qkv, kcache(h, g, l, 0), vcache(h, g, l, 0), att, part, B, H, h->cfg.max_len, 0, st,
                                    h->n_split, s, h->attn_group, 0, g == 1 ? -1 : 0));
+        if (att_lo) SFB_TRY(launch_split_lo(att, att_lo, (size_t)B * d, s));
+    }
     if (timed) {
         SFB_CUDA_TRY(cudaEventRecord((*h->ev)[h->ev_used + 1], s));
         h->ev_used += 2;
@@ -387,8 +391,7 @@ static int block_step(sfb200_ar *h, int g, int l, float *x, cudaStream_t s) {
     float *ff_lo = big ? WS_<float>(h, h->buf.ff_lo) : nullptr;
     SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN1_W, g, l), W_(h, SFB200_W_LN1_B, g, l), hb, B, d, s, h_lo));
     SFB_TRY(linear(h, SFB200_W_QKV_W, g, l, hb, W_(h, SFB200_W_QKV_B, g, l), nullptr, qkv, B, 3 * d, d, 0, s, h_lo));
-    SFB_TRY(attn_step(h, g, l, s));
-    if (big) SFB_TRY(launch_split_lo(att, att_lo, (size_t)B * d, s));
+    SFB_TRY(attn_step(h, g, l, s, att_lo));
     SFB_TRY(linear(h, SFB200_W_PROJ_W, g, l, att, W_(h, SFB200_W_PROJ_B, g, l), x, x, B, d, d, 0, s, att_lo));
     SFB_TRY(launch_layernorm(x, W_(h, SFB200_W_LN2_W, g, l), W_(h, SFB200_W_LN2_B, g, l), hb, B, d, s, h_lo));
     SFB_TRY(linear(h, SFB200_W_FC1_W, g, l, hb, W_(h, SFB200_W_FC1_B, g, l), nullptr, ff, B, 4 * d, d, 1, s, h_lo, ff_lo));

@@ -87,7 +87,7 @@ int set_chain_timeline(unsigned long long *buf);
 int launch_attn_decode(const float *qkv, float *kc, float *vc, float *out, float *part, int B, int H, int max_len, int pos,
                        const int32_t *st, int n_split, cudaStream_t s, int group = 1, int lcond = 0, int lcond_delta = 0);
 int launch_attn_grouped(const float *qkv, float *kc, float *vc, float *out, float *part, int *cnt, int B, int H, int max_len, int pos,
-                        const int32_t *st, int group, int lcond, int lcond_delta, cudaStream_t s);
+                        const int32_t *st, int group, int lcond, int lcond_delta, cudaStream_t s, float *out_lo = nullptr);
 int launch_attn_prefill(const float *qkv, float *kc, float *vc, float *out, int B, int H, int T, int max_len,
                         cudaStream_t s, const int32_t *rowmap = nullptr);
 int launch_sample(const SampleLaunch &p, cudaStream_t s);

@@ -150,7 +150,7 @@ __device__ __forceinline__ void ag_merge(const AgState (&st)[NQ], float *sm, flo
 // Publish partial state `sp_e` as part u of (row b, head h); the warp that delivers the last of the AG_PARTS parts combines them
 // (fixed order) into out[b][h*64 ..].  One warp per call; the memory fence and the atomic are paid once per part, at the end of
 // the CTA, by four warps in parallel.
-__device__ __forceinline__ void ag_publish(const float *sp_e, float *part, int *cnt, float *out, int b, int h, int H, int u) {
+__device__ __forceinline__ void ag_publish(const float *sp_e, float *part, int *cnt, float *out, float *out_lo, int b, int h, int H, int u) {
     const int lane = threadIdx.x & 31;
     float *p = part + (((size_t)b * H + h) * AG_PARTS + u) * AG_PSTRIDE;
     __stcg(reinterpret_cast<float2 *>(p + 2 * lane), *reinterpret_cast<const float2 *>(sp_e + 2 * lane));
@@ -182,7 +182,10 @@ __device__ __forceinline__ void ag_publish(const float *sp_e, float *part, int *
             a1 = fmaf(os[i].y, w, a1);
         }
         const float inv = 1.0f / L;
-        *reinterpret_cast<float2 *>(out + (size_t)b * H * 64 + h * 64 + 2 * lane) = make_float2(a0 * inv, a1 * inv);
+        const float o0 = a0 * inv, o1 = a1 * inv;
+        *reinterpret_cast<float2 *>(out + (size_t)b * H * 64 + h * 64 + 2 * lane) = make_float2(o0, o1);
+        // low part of the TF32 operand split, for a tc_big projection GEMM that reads it from memory
+        if (out_lo) *reinterpret_cast<float2 *>(out_lo + (size_t)b * H * 64 + h * 64 + 2 * lane) = make_float2(tf32_lo(o0), tf32_lo(o1));
         if (lane == 0) cnt[(size_t)b * H + h] = 0;     // ready for the next launch
     }
 }
@@ -192,7 +195,7 @@ constexpr int AG_THREADS = 160;     // warps 0-3 consume, warp 4 produces (TMA b
 template <int G>
 __global__ void __launch_bounds__(AG_THREADS) attn_grouped_kernel(const float *qkv, float *kcache, float *vcache, float *out, float *part,
                                                                   int *cnt, int H, int max_len, int pos_arg, const int32_t *st_dev,
-                                                                  int lcond_arg, int lcond_delta) {
+                                                                  int lcond_arg, int lcond_delta, float *out_lo) {
     pdl_trigger();
     extern __shared__ __align__(128) unsigned char ag_smem[];
     constexpr int RPC = G / 2;                                                       // rows whose own keys this CTA streams
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__(AG_THREADS) attn_grouped_kernel(const float *q
     // ---- publish: parts 0 .. G-1 = prefix half u of rows b0 + q; parts G + j = own keys (part index 2) of rows r0 + j
     for (int e = warp; e < NPART; e += 4) {
         const bool own = e >= G;
-        ag_publish(sp + e * AG_PSTRIDE, part, cnt, out, own ? r0 + (e - G) : b0 + e, h, H, own ? 2 : u);
+        ag_publish(sp + e * AG_PSTRIDE, part, cnt, out, out_lo, own ? r0 + (e - G) : b0 + e, h, H, own ? 2 : u);
     }
 }
 
@@ -293,22 +296,22 @@ constexpr int ag_smem_bytes() { return AG_NS * 2 * AG_TILE + G * 8 * AG_MRG * 4 
 
 template <int G>
 static int launch_ag(const float *qkv, float *kc, float *vc, float *out, float *part, int *cnt, int B, int H, int max_len, int pos,
-                     const int32_t *st, int lcond, int lcond_delta, cudaStream_t s) {
+                     const int32_t *st, int lcond, int lcond_delta, cudaStream_t s, float *out_lo) {
     static unsigned long long attr_done = 0;   // bit per device
     if (first_use_on_device(attr_done))
         SFB_CUDA_TRY(cudaFuncSetAttribute(attn_grouped_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, ag_smem_bytes<G>()));
     return launch_ex("attn_grouped", attn_grouped_kernel<G>, dim3(H, B / G, 2), dim3(AG_THREADS), ag_smem_bytes<G>(), s, dim3(1, 1, 1), qkv,
-                     kc, vc, out, part, cnt, H, max_len, pos, st, lcond, lcond_delta);
+                     kc, vc, out, part, cnt, H, max_len, pos, st, lcond, lcond_delta, out_lo);
 }
 
 int launch_attn_grouped(const float *qkv, float *kc, float *vc, float *out, float *part, int *cnt, int B, int H, int max_len, int pos,
-                        const int32_t *st, int group, int lcond, int lcond_delta, cudaStream_t s) {
+                        const int32_t *st, int group, int lcond, int lcond_delta, cudaStream_t s, float *out_lo) {
     if (group < 2 || B % group != 0 || !part || !cnt) return SFB200_E_ARG;
     switch (group) {
-        case 2: return launch_ag<2>(qkv, kc, vc, out, part, cnt, B, H, max_len, pos, st, lcond, lcond_delta, s);
-        case 4: return launch_ag<4>(qkv, kc, vc, out, part, cnt, B, H, max_len, pos, st, lcond, lcond_delta, s);
-        case 6: return launch_ag<6>(qkv, kc, vc, out, part, cnt, B, H, max_len, pos, st, lcond, lcond_delta, s);
-        case 8: return launch_ag<8>(qkv, kc, vc, out, part, cnt, B, H, max_len, pos, st, lcond, lcond_delta, s);
+        case 2: return launch_ag<2>(qkv, kc, vc, out, part, cnt, B, H, max_len, pos, st, lcond, lcond_delta, s, out_lo);
+        case 4: return launch_ag<4>(qkv, kc, vc, out, part, cnt, B, H, max_len, pos, st, lcond, lcond_delta, s, out_lo);
+        case 6: return launch_ag<6>(qkv, kc, vc, out, part, cnt, B, H, max_len, pos, st, lcond, lcond_delta, s, out_lo);
+        case 8: return launch_ag<8>(qkv, kc, vc, out, part, cnt, B, H, max_len, pos, st, lcond, lcond_delta, s, out_lo);
     }
     return SFB200_E_ARG;
 }

@@ -27,7 +27,7 @@ namespace sfb {
 using namespace tc;
 
 constexpr int BG_THREADS = 320;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: promotion + epilogue
-constexpr int BG_G = 2;                  // chunks per promotion group (24 MMAs per TMEM accumulation chain)
+constexpr int BG_G = 2;                  // chunks per promotion group (24 MMAs per TMEM accumulation chain; 4 costs 3e-5 on the logits)
 constexpr int BG_A_TILE = 128 * 32 * 4;  // 16 KB
 
 template <int BN>

@@ -103,6 +103,19 @@ def conv_prologue(sd, x, prefix="decoder.", wsplit=None, unet_mode="fp32", up_mo
     return x
 
 
+def pack_subpixel_weights(w):
+    """3x3x3 conv weight (Cout, Cin, 3, 3, 3) applied AFTER a nearest x2 upsampling -> (8 phases, 8 taps, Cout, Cin): output voxel
+    2q + p of an axis reads upsampled voxels 2q+p-1 .. 2q+p+1 = input voxels {q-1, q, q} (p = 0) or {q, q, q+1} (p = 1), so the three
+    taps collapse onto two input voxels (offsets p-1 and p) with summed weights.  The zero padding of the upsampled tensor coincides
+    with zero padding of the input.  Sums are formed in fp64 and rounded once."""
+    A = torch.zeros(2, 2, 3, dtype=torch.float64, device=w.device)     # A[p, t, d] = 1 iff original tap d lands on low-res tap t
+    A[0, 0, 0] = A[0, 1, 1] = A[0, 1, 2] = 1
+    A[1, 0, 0] = A[1, 0, 1] = A[1, 1, 2] = 1
+    ws = torch.einsum("oidef,ptd,quE,rvf->pqrtuvoi".replace("E", "e"), w.double(), A, A, A)
+    co, ci = w.shape[:2]
+    return ws.reshape(8, 8, co, ci).float().contiguous()
+
+
 class ConvPrologueTC:
     """UNet3D + Upsampler (vqdif/unet3d.py:449-474, updown.py:119-132) on this library's kernels (csrc/conv_tc.cu), all
     tensors channels-last (B, D, H, W, C): tcgen05 3xTF32 implicit-GEMM convolutions fed by TMA, GroupNorm statistics
@@ -131,6 +144,12 @@ class ConvPrologueTC:
             conv(n, sd[n + "conv.weight"])
             self.p[n + "gn"] = (sd[n + "groupnorm.weight"].contiguous(), sd[n + "groupnorm.bias"].contiguous())
         conv(u + "final", sd[u + "final_conv.weight"])
+        # the two convolutions that follow an upsampling run in sub-pixel form on the low-resolution input (27/8 fewer FLOPs)
+        for k in (1, 4):
+            n = f"{prefix}upsampler.blocks.{k}."
+            w = sd[n + "conv.weight"]
+            wp = pack_subpixel_weights(w).reshape(64 * w.shape[0], w.shape[1])
+            self.p[n + "up"] = (wp, ops.split_lo(wp), w.shape[1], w.shape[0], 8)
         self.final_bias = sd[u + "final_conv.bias"].contiguous()
         self.u, self.up = u, prefix + "upsampler."
 
@@ -139,8 +158,10 @@ class ConvPrologueTC:
         return torch.zeros(B, C, 2, dtype=torch.float64, device=self.device)
 
     def _conv(self, hi, lo, key, B, R, relu=True, bias=None, want_stats=True):
+        """R = INPUT resolution; keys ending in "up" are sub-pixel convolutions whose output has resolution 2R."""
         wp, wl, ci, co, taps = self.p[key]
-        out = torch.empty(B, R, R, R, co, dtype=torch.float32, device=self.device)
+        Ro = 2 * R if taps == 8 else R
+        out = torch.empty(B, Ro, Ro, Ro, co, dtype=torch.float32, device=self.device)
         st = self._stats(B, co) if want_stats else None
         _lib.check(self.lib.sfb200_conv3d_tc(_lib.ptr(hi), _lib.ptr(lo), _lib.ptr(wp), _lib.ptr(wl), _lib.ptr(bias), _lib.ptr(out),
                                              _lib.ptr(st), B, R, R, R, ci, co, taps, int(relu), _lib.stream_ptr()), "sfb200_conv3d_tc")
@@ -206,14 +227,15 @@ class ConvPrologueTC:
         f, _ = self._conv(hi, lo, u + "final", B, r, relu=False, bias=self.final_bias, want_stats=False)
         # ---- Upsampler: 2 x [nearest x2, 'crg', 'crg'] = conv -> ReLU -> GroupNorm (updown.py:79-132); the GroupNorm of a layer
         #      is applied by the next layer's prep pass (or by the final pass that writes the feature grid)
+        #      the upsampling is never materialised: the conv after it runs in sub-pixel form on the low-resolution tensor
+        hi, lo = self._prep(B, r, f, None, 1.0)
+        a, sa = self._conv(hi, lo, self.up + "blocks.1.up", B, r)
         R = 2 * r
-        hi, lo = self._prep(B, R, f, None, 1.0, sh0=1)
-        a, sa = self._conv(hi, lo, self.up + "blocks.1.", B, R)
         hi, lo = self._prep(B, R, a, sa, R ** 3, gn=self.up + "blocks.1.gn")
         a, sa = self._conv(hi, lo, self.up + "blocks.2.", B, R)
-        hi, lo = self._prep(B, 2 * R, a, sa, R ** 3, sh0=1, gn=self.up + "blocks.2.gn")
+        hi, lo = self._prep(B, R, a, sa, R ** 3, gn=self.up + "blocks.2.gn")
+        a, sa = self._conv(hi, lo, self.up + "blocks.4.up", B, R)
         R *= 2
-        a, sa = self._conv(hi, lo, self.up + "blocks.4.", B, R)
         hi, lo = self._prep(B, R, a, sa, R ** 3, gn=self.up + "blocks.4.gn")
         a, sa = self._conv(hi, lo, self.up + "blocks.5.", B, R)
         grid, _ = self._prep(B, R, a, sa, R ** 3, gn=self.up + "blocks.5.gn", want_lo=False)

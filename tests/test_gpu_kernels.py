@@ -331,6 +331,31 @@ def test_conv3d_tc(cuda, B, R, Cin, Cout, k):
     assert (st - s_ref).abs().max() < 1e-3 * max(1.0, s_ref.abs().max().item())
 
 
+@pytest.mark.parametrize("B,R,Cin,Cout", [(2, 16, 128, 64), (1, 32, 64, 32), (3, 4, 64, 128)])
+def test_conv3d_tc_subpixel_after_upsample(cuda, B, R, Cin, Cout):
+    """[nearest x2 -> 3x3x3 conv pad 1 -> ReLU] in sub-pixel form (8 phases x 8 summed taps on the low-resolution input) against
+    torch fp64 on the materialised upsampled tensor, incl. the epilogue sums."""
+    from shapeformer_b200 import _lib
+    from shapeformer_b200.decoder import pack_subpixel_weights
+    lib = _lib.load()
+    x = rnd(B, R, R, R, Cin, seed=1)
+    w = rnd(Cout, Cin, 3, 3, 3, seed=2, scale=1.0 / math.sqrt(Cin * 27))
+    hi = x.to(cuda).contiguous()
+    lo = ops.split_lo(hi)
+    wp = pack_subpixel_weights(w.to(cuda)).reshape(64 * Cout, Cin).contiguous()
+    wl = ops.split_lo(wp)
+    out = torch.empty(B, 2 * R, 2 * R, 2 * R, Cout, device=cuda)
+    st = torch.zeros(B, Cout, 2, dtype=torch.float64, device=cuda)
+    _lib.check(lib.sfb200_conv3d_tc(_lib.ptr(hi), _lib.ptr(lo), _lib.ptr(wp), _lib.ptr(wl), None, _lib.ptr(out), _lib.ptr(st),
+                                    B, R, R, R, Cin, Cout, 8, 1, _lib.stream_ptr()), "conv3d_tc")
+    up = F.interpolate(x.permute(0, 4, 1, 2, 3).double(), scale_factor=2, mode="nearest")
+    ref = F.relu(F.conv3d(up, w.double(), padding=1)).permute(0, 2, 3, 4, 1)
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err < 4e-6 * max(1.0, ref.abs().max().item()), err
+    s_ref = torch.stack([ref.sum((1, 2, 3)), (ref * ref).sum((1, 2, 3))], -1)
+    assert (st.cpu() - s_ref).abs().max() < 1e-3 * max(1.0, s_ref.abs().max().item())
+
+
 def test_conv_prep_groupnorm_upsample_concat_and_pool(cuda):
     """conv_prep: GroupNorm(8) from per-channel sums over the CONCATENATION of a skip tensor and a x2-upsampled tensor, operand
     split on store; pool_stats: max-pool 2 + sums — against torch."""
