@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--lcond", type=int, default=256)
     ap.add_argument("--ar-steps", type=int, default=512)
     ap.add_argument("--grid", type=int, default=64, help="query grid resolution per axis")
+    ap.add_argument("--cloud-points", type=int, default=8192,
+                    help="points per synthetic partial cloud fed to the encoder stage (one cloud per shape; 0 skips the stage)")
     ap.add_argument("--top-k", type=int, default=50)
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"])
     ap.add_argument("--tiny", action="store_true", help="tiny transformer (smoke runs; NOT a valid bench number)")
@@ -251,7 +253,9 @@ def main():
     workload = {"workload": (f"{what}: {per_gpu} rows per GPU ({rows_total // args.sample_n} shapes x sample_n "
                              f"{args.sample_n} in total), L_cond {args.lcond}, {args.ar_steps} AR steps fixed-length "
                              f"(masks off), top_k {args.top_k}, top_p {args.top_p:g}, T 1"
-                             f"{', best_in_first' if best_first else ''}, + {args.grid}^3 decode"),
+                             f"{', best_in_first' if best_first else ''}, + {args.grid}^3 decode"
+                             + (f"; encoder stage: {rows_total // args.sample_n} partial clouds x {args.cloud_points} points -> "
+                                f"code grids + tuples every step" if args.cloud_points > 0 else "")),
                 "rows_per_gpu": per_gpu, "rows_total": rows_total, "l_cond": args.lcond, "ar_steps": args.ar_steps,
                 "grid": args.grid, "transformer": "tiny (INVALID as a bench number)" if args.tiny else "shipped 20+4 x 1024 (325M)",
                 "weights": "synthetic seed 314 (reference init)", "parallelism": f"rows sharded x{world} ({args.mode})",
@@ -301,7 +305,10 @@ def main():
                         representer_opt={"class": pre + "shapeformer.representers.AR_N",
                                          "kwargs": dict(block_size=cfg["block_size"], end_tokens=list(END),
                                                         mask_invalid=False, mask_invalid_completion=False, vqvae_opt=None)})
-    vq = VQDIF(decoder_opt={"class": pre + "vqdif.dec.LocalDecoder",
+    vq = VQDIF(encoder_opt={"class": pre + "vqdif.enc.LocalPoolPointnet",
+                            "kwargs": dict(hidden_dim=32, plane_type="grid", grid_resolution=64, c_dim=32, downsampler=True,
+                                           downsampler_kwargs=dict(in_channels=32, downsample_steps=2))},
+               decoder_opt={"class": pre + "vqdif.dec.LocalDecoder",
                             "kwargs": dict(sample_mode="bilinear", hidden_size=32, c_dim=32, unet3d=True,
                                            unet3d_kwargs=dict(num_levels=3, f_maps=128, in_channels=128, out_channels=128),
                                            upsampler=True, upsampler_kwargs=dict(in_channels=128, upsampler_steps=2))},
@@ -322,14 +329,30 @@ def main():
     xtg_dev = xtg_host.to(dev)
     empty = torch.full((B,), 17, dtype=torch.int64, device=dev)
     eng = vq.engine()
+    # cfg 5's first stage: one synthetic partial cloud per shape -> LocalPoolPointnet encoder -> quantiser -> (pos, val) tuples
+    # (csrc/enc_kernels.cu).  Its tuples have a data-dependent length per shape while the sampler takes ONE conditioning length
+    # per batch (a deployment buckets shapes by length), so the stage is run, timed and checked inside every step, its batch
+    # mode code fills the unsampled cells of the decoder input, and the AR conditioning stays the fixed-length synthetic one.
+    n_shapes = B // args.sample_n
+    clouds_host = synth.partial_cloud(n_shapes, T=args.cloud_points, seed=2000 + rank).pin_memory() if args.cloud_points > 0 else None
+    clouds_dev = clouds_host.to(dev) if clouds_host is not None else None
+
+    def encode_stage(clouds):
+        if clouds is None:
+            return empty
+        enc = vq.point_encoder().quantize_cloud(clouds)
+        c = enc["c_indices"]
+        assert c.shape[0] == n_shapes and c.shape[2] == 2 and 2 <= c.shape[1] <= 406
+        return enc["empty_index"].reshape(1).expand(B).contiguous()
     use_graph = {"auto": True, "on": True, "off": False}[args.graph]
     sampler = model.transformer.sampler(B, Lc, S, END, keep_history=False)
     skw = dict(top_k=args.top_k, top_p=args.top_p, temperature=1.0, best_in_first=best_first, mask_invalid=False,
                mask_invalid_completion=False, stop_early=False)
 
     def step_value():
+        fill = encode_stage(clouds_dev)
         x, _ = sampler.sample(c_dev, S, use_graph=use_graph, **skw)
-        dense = eng.tokens_to_dense(x, empty)
+        dense = eng.tokens_to_dense(x, fill)
         occ = eng.occupancy(dense, xtg_dev)
         if world > 1:      # ONE all-gather of the per-row outputs per batch (row blocks may be unequal in strong mode)
             sdist.gather_rows(x.contiguous())
@@ -439,7 +462,8 @@ def main():
                     "note": "achieved counts the ALGORITHMIC 30,976 FLOP/point (SURVEY §8d); the kernel executes 3x that as "
                             "3xTF32 split products (executed_frac); tensor_pipe_pct_ncu = sm__pipe_tensor_cycles_active of the "
                             "committed ncu capture"}
-        breakdown = {"ar_pass_eager_ms": pe0.elapsed_time(pe1), "attention_ms": a_ms.value,
+        t_enc = ev_time(lambda: encode_stage(clouds_dev))[0] if clouds_dev is not None else 0.0
+        breakdown = {"ar_pass_eager_ms": pe0.elapsed_time(pe1), "attention_ms": a_ms.value, "encoder_stage_ms": t_enc,
                      "conv_prologue_ms": t_pro * B / Bd, "point_kernel_ms": t_pts * B / Bd,
                      "note": f"decoder times = one {Bd}-shape pass x {B / Bd:g} passes"}
 
@@ -455,11 +479,12 @@ def main():
         occ_host = torch.empty(B, R ** 3, dtype=torch.float32).pin_memory()
 
         def step_e2e():
+            fill = encode_stage(clouds_host.to(dev, non_blocking=True) if clouds_host is not None else None)
             c = c_host.to(dev, non_blocking=True)
             out_x, x, hist = model.sample(c_indices=c, z_indices=c[:, :0], max_steps=S, temperature=1.0, sample=True,
                                           best_in_first=best_first, top_k=args.top_k, top_p=args.top_p)
             # NB: early exit is part of the API; with masks off and random weights no row ends, so all S steps run
-            dense = eng.tokens_to_dense(out_x, empty)
+            dense = eng.tokens_to_dense(out_x, fill)
             occ = vq.engine().occupancy(dense, xtg_host.to(dev, non_blocking=True))
             tok_host.copy_(out_x, non_blocking=True)
             occ_host.copy_(occ, non_blocking=True)
@@ -470,9 +495,10 @@ def main():
         ms_e, _ = timed(step_e2e, n_e2e)
         hist_bytes = 2 * B * S * 4097 * 4
         e2e = {"value": rows_total * n_e2e / (ms_e * 1e-3), "unit": "shapes/s", "steps": n_e2e,
-               "h2d_bytes_per_step": int(c_host.numel() * 8 + xtg_host.numel() * 4),
+               "h2d_bytes_per_step": int(c_host.numel() * 8 + xtg_host.numel() * 4 +
+                                         (clouds_host.numel() * 4 if clouds_host is not None else 0)),
                "d2h_bytes_per_step": int(tok_host.numel() * 8 + occ_host.numel() * 4 + hist_bytes),
-               "api": "ShapeFormer.sample(...) [fresh token tensor + the reference's CPU logits history in fresh tensors, streamed "
+               "api": "VQDIF.point_encoder().quantize_cloud(clouds) -> ShapeFormer.sample(...) [fresh token tensor + the reference's CPU logits history in fresh tensors, streamed "
                       "to the host chunk by chunk while the next chunk is computed] -> tokens_to_dense -> VQDIF occupancy; pinned "
                       "host buffers for inputs/outputs"}
         model.history_device = None

@@ -123,3 +123,29 @@ def test_full_checkpoint_loads_through_the_parent_and_invalidates_caches():
     assert model.transformer._packed is None and model.transformer._samplers == {} and vq._engine is None
     assert torch.equal(model.transformer.tok_embs[0].weight, ckpt["transformer.tok_embs.0.weight"])
     assert torch.equal(vq.decoder.fc_out.weight, vsd["decoder.fc_out.weight"])
+
+
+def test_subpixel_weight_packing_matches_upsample_then_conv():
+    """decoder.pack_subpixel_weights (host logic of the sub-pixel convolutions, csrc/conv_tc.cu taps = 8): 8 phases x 8 summed taps on
+    the low-resolution input == nearest x2 upsampling followed by the 3x3x3 convolution with zero padding (updown.py:119-132)."""
+    import torch.nn.functional as F
+    from shapeformer_b200.decoder import pack_subpixel_weights
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(5, 3, 3, 3, 3, generator=g)
+    x = torch.randn(2, 3, 4, 4, 4, generator=g, dtype=torch.float64)
+    ref = F.conv3d(F.interpolate(x, scale_factor=2, mode="nearest"), w.double(), padding=1)
+    wp = pack_subpixel_weights(w).double().reshape(2, 2, 2, 2, 2, 2, 5, 3)
+    xp = F.pad(x, (1, 1, 1, 1, 1, 1))
+    out = torch.zeros_like(ref)
+    for pz in range(2):
+        for py in range(2):
+            for px in range(2):
+                acc = 0
+                for tz in range(2):
+                    for ty in range(2):
+                        for tx in range(2):
+                            dz, dy, dx = pz - 1 + tz, py - 1 + ty, px - 1 + tx
+                            sl = xp[:, :, 1 + dz:5 + dz, 1 + dy:5 + dy, 1 + dx:5 + dx]
+                            acc = acc + torch.einsum("bizyx,oi->bozyx", sl, wp[pz, py, px, tz, ty, tx])
+                out[:, :, pz::2, py::2, px::2] = acc
+    assert (out - ref).abs().max() < 1e-5
