@@ -5,6 +5,8 @@
 // tensor, which needs logits within ~1e-5 of the fp32 PyTorch path.
 #include <cooperative_groups.h>
 
+#include <stdlib.h>
+
 #include "ar_kernels.cuh"
 
 namespace cg = cooperative_groups;
@@ -1074,6 +1076,10 @@ int launch_attn_decode(const float *qkv, float *kc, float *vc, float *out, float
 int launch_attn_prefill(const float *qkv, float *kc, float *vc, float *out, int B, int H, int T, int max_len,
                         cudaStream_t s, const int32_t *rowmap) {
     if (T <= 0) return SFB200_OK;
+    // >= 32 positions: the tcgen05 kernel (attn_prefill_tc.cu: QK^T and PV on the tensor cores); SFB200_PREFILL_TC=0 keeps the FFMA one
+    static int use_tc = -1;
+    if (use_tc < 0) { const char *e = getenv("SFB200_PREFILL_TC"); use_tc = (e && e[0] == '0') ? 0 : 1; }
+    if (use_tc && T >= 32) return launch_attn_prefill_tc(qkv, kc, vc, out, B, H, T, max_len, s, rowmap);
     return launch_ex("attn_prefill", attn_prefill_kernel, dim3(H, B, (T + 7) / 8), dim3(256), 0, s, dim3(1, 1, 1), qkv, kc, vc, out, H,
                      T, max_len, rowmap);
 }

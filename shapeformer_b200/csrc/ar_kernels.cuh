@@ -90,6 +90,8 @@ int launch_attn_grouped(const float *qkv, float *kc, float *vc, float *out, floa
                         const int32_t *st, int group, int lcond, int lcond_delta, cudaStream_t s, float *out_lo = nullptr);
 int launch_attn_prefill(const float *qkv, float *kc, float *vc, float *out, int B, int H, int T, int max_len,
                         cudaStream_t s, const int32_t *rowmap = nullptr);
+int launch_attn_prefill_tc(const float *qkv, float *kc, float *vc, float *out, int B, int H, int T, int max_len, cudaStream_t s,
+                           const int32_t *rowmap = nullptr);
 int launch_sample(const SampleLaunch &p, cudaStream_t s);
 
 }  // namespace sfb

@@ -171,8 +171,10 @@ def test_attn_decode(cuda, B, H, pos, n_split):
     assert torch.equal(kc.cpu(), Kr) and torch.equal(vc.cpu(), Vr)   # append only touched `pos`
 
 
-@pytest.mark.parametrize("B,H,T", [(1, 2, 1), (2, 2, 9), (2, 16, 64), (3, 4, 255)])
+@pytest.mark.parametrize("B,H,T", [(1, 2, 1), (2, 2, 9), (2, 16, 64), (3, 4, 255), (2, 3, 32), (2, 16, 256), (1, 2, 300), (2, 2, 129)])
 def test_attn_prefill(cuda, B, H, T):
+    """Causal prefill attention + cache fill against torch fp32: the FFMA kernel below 32 positions, the tcgen05 kernel
+    (QK^T and PV as 3xTF32 tensor-core GEMMs, P kept in tensor memory) from 32 positions on, incl. ragged last tiles."""
     max_len, d = 300, H * 64
     qkv = rnd(B, T, 3 * d, seed=5)
     kc, vc = torch.zeros(B, H, max_len, 64, device=cuda), torch.zeros(B, H, max_len, 64, device=cuda)
