@@ -279,6 +279,8 @@ def main():
         return
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
+    # torchrun exports OMP_NUM_THREADS=1; the e2e arm's host copies of the logits history (8.6 GB per batch) want a few threads
+    torch.set_num_threads(max(1, min(16, (os.cpu_count() or 1) // max(world, 1))))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     torch.backends.cuda.matmul.allow_tf32 = False

@@ -344,6 +344,22 @@ int sfb200_pool_stats(const float *src, float *dst, double *stats, int B, int Zo
 int sfb200_gather_codes_cl(const int64_t *idx, const float *codebook, float *out, double *stats, int B, int cells, int C,
                            int n_codes, void *stream);
 
+/* ---- occupancy grid -> triangle mesh (csrc/mesh_kernels.cu): the step after decode_sample_indices in the reference,
+ * geoutil.array2mesh (xgutils/geoutil.py:175-233) -> PyMCubes marching_cubes.  PyMCubes is not under the reference tree; this is
+ * marching TETRAHEDRA on the Kuhn subdivision of every cube (same level set, linear interpolation, watertight, another
+ * triangulation).  grid: (R, R, R) fp32 indexed [i][j][k]; vertices come out in grid-index coordinates.
+ *   1. sfb200_mesh_mark_edges    flag (R^3 * 7) int32 = 1 where the level set crosses edge (vertex, direction)
+ *   2. caller: vid = exclusive scan of flag, V = total
+ *   3. sfb200_mesh_emit_vertices verts (V, 3) fp32
+ *   4. sfb200_mesh_count_faces   count ((R-1)^3) int32 triangles per cube;  caller: foff = exclusive scan, F = total
+ *   5. sfb200_mesh_emit_faces    faces (F, 3) int32, normals pointing from grid > thresh to grid <= thresh */
+int sfb200_mesh_mark_edges(const float *grid, int R, float thresh, int32_t *flag, void *stream);
+int sfb200_mesh_emit_vertices(const float *grid, int R, float thresh, const int32_t *flag, const int32_t *vid, float *verts,
+                              void *stream);
+int sfb200_mesh_count_faces(const float *grid, int R, float thresh, int32_t *count, void *stream);
+int sfb200_mesh_emit_faces(const float *grid, int R, float thresh, const int32_t *vid, const int32_t *foff, const float *verts,
+                           int32_t *faces, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

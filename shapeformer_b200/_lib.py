@@ -67,6 +67,10 @@ SIGNATURES = {
                                         ctypes.c_int, vp]),
     "sfb200_pool_stats": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
     "sfb200_gather_codes_cl": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
+    "sfb200_mesh_mark_edges": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_float, vp, vp]),
+    "sfb200_mesh_emit_vertices": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_float, vp, vp, vp, vp]),
+    "sfb200_mesh_count_faces": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_float, vp, vp]),
+    "sfb200_mesh_emit_faces": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_float, vp, vp, vp, vp, vp]),
     "sfb200_tokens_to_dense": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64,
                                               ctypes.c_int64, vp]),
     "sfb200_encoder_workspace_bytes": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),

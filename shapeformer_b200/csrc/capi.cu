@@ -7,6 +7,7 @@
 #include "conv_tc.cuh"
 #include "decoder_kernels.cuh"
 #include "enc_kernels.cuh"
+#include "mesh_kernels.cuh"
 
 #include <atomic>
 namespace sfb {
@@ -198,6 +199,21 @@ int sfb200_pool_stats(const float *src, float *dst, double *stats, int B, int Zo
 int sfb200_gather_codes_cl(const int64_t *idx, const float *codebook, float *out, double *stats, int B, int cells, int C,
                            int n_codes, void *stream) {
     return launch_gather_codes_cl(idx, codebook, out, stats, B, cells, C, n_codes, as_stream(stream));
+}
+
+int sfb200_mesh_mark_edges(const float *grid, int R, float thresh, int32_t *flag, void *stream) {
+    return launch_mesh_mark_edges(grid, R, thresh, flag, as_stream(stream));
+}
+int sfb200_mesh_emit_vertices(const float *grid, int R, float thresh, const int32_t *flag, const int32_t *vid, float *verts,
+                              void *stream) {
+    return launch_mesh_emit_vertices(grid, R, thresh, flag, vid, verts, as_stream(stream));
+}
+int sfb200_mesh_count_faces(const float *grid, int R, float thresh, int32_t *count, void *stream) {
+    return launch_mesh_count_faces(grid, R, thresh, count, as_stream(stream));
+}
+int sfb200_mesh_emit_faces(const float *grid, int R, float thresh, const int32_t *vid, const int32_t *foff, const float *verts,
+                           int32_t *faces, void *stream) {
+    return launch_mesh_emit_faces(grid, R, thresh, vid, foff, verts, faces, as_stream(stream));
 }
 
 }  // extern "C"
