@@ -192,13 +192,16 @@ __device__ __forceinline__ void ag_publish(const float *sp_e, float *part, int *
 
 constexpr int AG_THREADS = 160;     // warps 0-3 consume, warp 4 produces (TMA bulk copies)
 
-template <int G>
+template <int G, bool MONO>
 __global__ void __launch_bounds__(AG_THREADS) attn_grouped_kernel(const float *qkv, float *kcache, float *vcache, float *out, float *part,
                                                                   int *cnt, int H, int max_len, int pos_arg, const int32_t *st_dev,
                                                                   int lcond_arg, int lcond_delta, float *out_lo) {
     pdl_trigger();
     extern __shared__ __align__(128) unsigned char ag_smem[];
-    constexpr int RPC = G / 2;                                                       // rows whose own keys this CTA streams
+    // MONO (large batches: heads x groups alone fill the GPU several times): ONE CTA per (head, group) streams the whole prefix
+    // and the own keys of all G rows, and combines the two states of every row in shared memory — no partials in global memory,
+    // no fence, no arrival counter.  Otherwise two CTAs per (head, group) split the work (single co-resident wave at 64 rows).
+    constexpr int RPC = MONO ? G : G / 2;                                            // rows whose own keys this CTA streams
     constexpr int NPART = G + RPC;                                                   // partial states this CTA publishes
     unsigned char *ring = ag_smem;                                                   // [NS][K tile | V tile]
     float *sm = reinterpret_cast<float *>(ag_smem + AG_NS * 2 * AG_TILE);            // [G][8][AG_MRG] merge staging
@@ -219,7 +222,7 @@ __global__ void __launch_bounds__(AG_THREADS) attn_grouped_kernel(const float *q
     const int b0 = grp * G, r0 = b0 + u * RPC;
     int mid = ((shared_end / 2) + AG_TK - 1) / AG_TK * AG_TK;
     if (mid > shared_end) mid = shared_end;
-    const int p_beg = u == 0 ? 0 : mid, p_end = u == 0 ? mid : shared_end;
+    const int p_beg = (MONO || u == 0) ? 0 : mid, p_end = (!MONO && u == 0) ? mid : shared_end;
 
     if (warp == 4) {
         // ================================ producer: every tile of every segment, in order ================================
@@ -284,6 +287,22 @@ __global__ void __launch_bounds__(AG_THREADS) attn_grouped_kernel(const float *q
         ag_stream<1>(st, q4, shared_end, pos, ring, full, empty, it);
         ag_merge<1>(st, sm, sp, G + j);
     }
+    if (MONO) {
+        // ---- combine in place: row q = prefix state sp[q] + own state sp[G + q] (fixed order -> deterministic)
+        for (int q = warp; q < G; q += 4) {
+            const float *pa = sp + q * AG_PSTRIDE, *pb = sp + (G + q) * AG_PSTRIDE;
+            const float ma = pa[64], mb = pb[64], MM = fmaxf(ma, mb);
+            const float wa = (ma == -INFINITY) ? 0.f : expf(ma - MM), wb = (mb == -INFINITY) ? 0.f : expf(mb - MM);
+            const float L = fmaf(pb[65], wb, pa[65] * wa);
+            const float2 oa = *reinterpret_cast<const float2 *>(pa + 2 * lane), ob = *reinterpret_cast<const float2 *>(pb + 2 * lane);
+            const float inv = 1.0f / L;
+            const float o0 = fmaf(ob.x, wb, oa.x * wa) * inv, o1 = fmaf(ob.y, wb, oa.y * wa) * inv;
+            const size_t off = (size_t)(b0 + q) * H * 64 + h * 64 + 2 * lane;
+            *reinterpret_cast<float2 *>(out + off) = make_float2(o0, o1);
+            if (out_lo) *reinterpret_cast<float2 *>(out_lo + off) = make_float2(tf32_lo(o0), tf32_lo(o1));
+        }
+        return;
+    }
     // ---- publish: parts 0 .. G-1 = prefix half u of rows b0 + q; parts G + j = own keys (part index 2) of rows r0 + j
     for (int e = warp; e < NPART; e += 4) {
         const bool own = e >= G;
@@ -292,16 +311,22 @@ __global__ void __launch_bounds__(AG_THREADS) attn_grouped_kernel(const float *q
 }
 
 template <int G>
-constexpr int ag_smem_bytes() { return AG_NS * 2 * AG_TILE + G * 8 * AG_MRG * 4 + (G + G / 2) * AG_PSTRIDE * 4 + 2 * AG_NS * 8; }
+constexpr int ag_smem_bytes() { return AG_NS * 2 * AG_TILE + G * 8 * AG_MRG * 4 + 2 * G * AG_PSTRIDE * 4 + 2 * AG_NS * 8; }
 
 template <int G>
 static int launch_ag(const float *qkv, float *kc, float *vc, float *out, float *part, int *cnt, int B, int H, int max_len, int pos,
                      const int32_t *st, int lcond, int lcond_delta, cudaStream_t s, float *out_lo) {
     static unsigned long long attr_done = 0;   // bit per device
-    if (first_use_on_device(attr_done))
-        SFB_CUDA_TRY(cudaFuncSetAttribute(attn_grouped_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, ag_smem_bytes<G>()));
-    return launch_ex("attn_grouped", attn_grouped_kernel<G>, dim3(H, B / G, 2), dim3(AG_THREADS), ag_smem_bytes<G>(), s, dim3(1, 1, 1), qkv,
-                     kc, vc, out, part, cnt, H, max_len, pos, st, lcond, lcond_delta, out_lo);
+    if (first_use_on_device(attr_done)) {
+        SFB_CUDA_TRY(cudaFuncSetAttribute(attn_grouped_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ag_smem_bytes<G>()));
+        SFB_CUDA_TRY(cudaFuncSetAttribute(attn_grouped_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ag_smem_bytes<G>()));
+    }
+    // one CTA per (head, group) once those alone fill the GPU's CTA slots about twice; two CTAs per (head, group) below that
+    if (H * (B / G) >= 1024)
+        return launch_ex("attn_grouped", attn_grouped_kernel<G, true>, dim3(H, B / G, 1), dim3(AG_THREADS), ag_smem_bytes<G>(), s,
+                         dim3(1, 1, 1), qkv, kc, vc, out, part, cnt, H, max_len, pos, st, lcond, lcond_delta, out_lo);
+    return launch_ex("attn_grouped", attn_grouped_kernel<G, false>, dim3(H, B / G, 2), dim3(AG_THREADS), ag_smem_bytes<G>(), s,
+                     dim3(1, 1, 1), qkv, kc, vc, out, part, cnt, H, max_len, pos, st, lcond, lcond_delta, out_lo);
 }
 
 int launch_attn_grouped(const float *qkv, float *kc, float *vc, float *out, float *part, int *cnt, int B, int H, int max_len, int pos,

@@ -72,11 +72,12 @@ def test_bench_batch_shipped_model_long_run(cuda):
 
 def test_large_batch_decode_path(cuda):
     """Decode batches of more than 64 rows (the default bench batch is 512) leave the persistent chain kernel for the TMA-fed
-    large-M GEMM (csrc/tc_big.cu) + LayerNorm / split kernels: 160 rows = 40 shapes x sample_n 4 of the shipped model, tokens
-    bit-exact against the KV-cached oracle."""
+    large-M GEMM (csrc/tc_big.cu) + LayerNorm / split kernels, and — from 1024 (head, group) pairs on — the one-CTA-per-(head,
+    group) form of the grouped attention: 256 rows = 64 shapes x sample_n 4 of the shipped model, tokens bit-exact against the
+    KV-cached oracle."""
     cfg = synth.SHIPPED_GPT
     sd = synth.gpt_state_dict(cfg, seed=314, peaky=True)
-    B, n, Lc, steps = 160, 4, 64, 40
+    B, n, Lc, steps = 256, 4, 64, 32
     c = synth.cond_indices(B // n, Lc, seed=2000).repeat_interleave(n, 0)
     noise = util.noise_from_seed(19, steps, B, 4097)
     worst = run_pair(cuda, cfg, sd, c, steps, 50, 0.0, True, noise)

@@ -131,7 +131,8 @@ def _ref_attn(q, K, V):
 
 
 @pytest.mark.parametrize("B,H,G,shared,pos", [(4, 2, 4, 0, 0), (4, 2, 4, 5, 5), (8, 16, 4, 256, 511), (6, 3, 2, 33, 40),
-                                               (8, 2, 8, 17, 100), (12, 4, 6, 31, 32), (64, 16, 4, 256, 300), (4, 2, 2, 100, 60)])
+                                               (8, 2, 8, 17, 100), (12, 4, 6, 31, 32), (64, 16, 4, 256, 300), (4, 2, 2, 100, 60),
+                                               (256, 16, 4, 64, 100), (128, 16, 2, 33, 33)])
 def test_attn_decode_grouped(cuda, B, H, G, shared, pos):
     """Grouped decode attention (shared prefix scored once per group from the leader's cache rows, TMA-staged tiles, partial
     states merged by the last arriver) against torch fp32 on the full per-row caches; appends the new K/V."""
