@@ -21,12 +21,12 @@ class _HistoryStreamer:
     _ring = {}          # (B, chunk, V tuple) -> [pinned (2 slots) per tuple element], reused across calls (never returned)
     _side = {}          # device index -> copy stream
 
-    def __init__(self, sampler, B):
+    def __init__(self, sampler, B, max_steps):
         self.s, self.B = sampler, B
         self.V = list(sampler.spec["vocab_sizes"])
         self.dev = sampler.device
         self.views = sampler.history_views(B)
-        self.out = [torch.empty(B, sampler.max_steps, v, dtype=torch.float32) for v in self.V]     # fresh, pageable
+        self.out = [torch.empty(B, min(int(max_steps), sampler.max_steps), v, dtype=torch.float32) for v in self.V]     # fresh, pageable
         key = (B, sampler.chunk_steps, tuple(self.V))
         ring = _HistoryStreamer._ring.get(key)
         if ring is None:
@@ -105,7 +105,7 @@ class ShapeFormer(nn.Module):
         s = self.transformer.sampler(B, L_c, max_steps, self.end_tokens, keep_history=keep)
         stream_hist = keep and self.history_device == "cpu" and not self.zero_copy_outputs
         with torch.cuda.device(self.device):
-            streamer = _HistoryStreamer(s, B) if stream_hist else None
+            streamer = _HistoryStreamer(s, B, max_steps) if stream_hist else None
             x, hist = self._run_sampler(s, c_indices, max_steps, top_k, top_p, temperature, best_in_first, rep, noise,
                                         generator, streamer.on_chunk if streamer else None)
             if streamer:
