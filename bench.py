@@ -430,6 +430,8 @@ def main():
             roof = {"kernel": "attn_grouped_kernel (single-query attention over the KV cache + KV append; attn_decode_kernel for ungrouped rows)", "bound": "hbm", "achieved": ach,
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                     "traffic": ncu.get("dram_bytes_per_launch") if ncu else None,
+                    "traffic_position": ncu.get("position") if ncu else None,
+                    "traffic_algorithmic_bytes_at_position": ncu.get("algorithmic_bytes") if ncu else None,
                     "traffic_note": (f"ncu --set full capture of this kernel at position {ncu.get('position')} of the same batch: "
                                      f"dram read+write {ncu.get('dram_bytes_per_launch'):.4g} B vs algorithmic "
                                      f"{ncu.get('algorithmic_bytes'):.4g} B at that position "
