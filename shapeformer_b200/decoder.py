@@ -103,6 +103,14 @@ def conv_prologue(sd, x, prefix="decoder.", wsplit=None, unet_mode="fp32", up_mo
     return x
 
 
+def pack_conv_weights(w):
+    """Conv3d weight (Cout, Cin, k, k, k) -> the (k^3 * Cout, Cin) matrix conv3d_tc reads: row tap * Cout + co with
+    tap = (dz * k + dy) * k + dx, i.e. [tap][co][ci] (one K-major B tile per (tap, 32-channel chunk))."""
+    co, ci = w.shape[:2]
+    taps = w.shape[2] * w.shape[3] * w.shape[4]
+    return w.reshape(co, ci, taps).permute(2, 0, 1).contiguous().reshape(taps * co, ci)
+
+
 def pack_subpixel_weights(w):
     """3x3x3 conv weight (Cout, Cin, 3, 3, 3) applied AFTER a nearest x2 upsampling -> (8 phases, 8 taps, Cout, Cin): output voxel
     2q + p of an axis reads upsampled voxels 2q+p-1 .. 2q+p+1 = input voxels {q-1, q, q} (p = 0) or {q, q, q+1} (p = 1), so the three
@@ -132,7 +140,7 @@ class ConvPrologueTC:
         def conv(key, w):
             co, ci = w.shape[:2]
             taps = w.shape[2] * w.shape[3] * w.shape[4]
-            wp = w.reshape(co, ci, taps).permute(2, 0, 1).contiguous().reshape(taps * co, ci)     # [tap][co][ci]
+            wp = pack_conv_weights(w)
             self.p[key] = (wp, ops.split_lo(wp), ci, co, taps)
 
         u = prefix + "unet3d."

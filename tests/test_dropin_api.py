@@ -149,3 +149,24 @@ def test_subpixel_weight_packing_matches_upsample_then_conv():
                             acc = acc + torch.einsum("bizyx,oi->bozyx", sl, wp[pz, py, px, tz, ty, tx])
                 out[:, :, pz::2, py::2, px::2] = acc
     assert (out - ref).abs().max() < 1e-5
+
+
+def test_conv_weight_packing_is_the_implicit_gemm_of_conv3d():
+    """decoder.pack_conv_weights: out[voxel, co] = sum_{tap, ci} in[voxel + offset(tap), ci] * wp[tap * Cout + co, ci] with
+    tap = (dz*3 + dy)*3 + dx and zero padding — the contraction conv3d_tc_kernel runs — equals F.conv3d(padding=1)."""
+    import torch.nn.functional as F
+    from shapeformer_b200.decoder import pack_conv_weights
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(6, 4, 3, 3, 3, generator=g, dtype=torch.float64)
+    x = torch.randn(2, 4, 5, 5, 5, generator=g, dtype=torch.float64)
+    ref = F.conv3d(x, w, padding=1)
+    wp = pack_conv_weights(w).reshape(27, 6, 4)
+    xp = F.pad(x, (1, 1, 1, 1, 1, 1))
+    out = torch.zeros_like(ref)
+    for tap in range(27):
+        dz, dy, dx = tap // 9 - 1, (tap // 3) % 3 - 1, tap % 3 - 1
+        sl = xp[:, :, 1 + dz:6 + dz, 1 + dy:6 + dy, 1 + dx:6 + dx]
+        out += torch.einsum("bizyx,oi->bozyx", sl, wp[tap])
+    assert (out - ref).abs().max() < 1e-12
+    w1 = torch.randn(6, 4, 1, 1, 1, generator=g, dtype=torch.float64)
+    assert torch.equal(pack_conv_weights(w1), w1.reshape(6, 4))
